@@ -1,0 +1,21 @@
+# Builds libpistoseg_b200.so (sm_100a only) in-tree.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Ipistoseg_b200/csrc
+SRCS      := $(wildcard pistoseg_b200/csrc/*.cu)
+OBJS      := $(patsubst pistoseg_b200/csrc/%.cu,build/%.o,$(SRCS))
+LIB       := pistoseg_b200/libpistoseg_b200.so
+
+all: $(LIB)
+
+build/%.o: pistoseg_b200/csrc/%.cu $(wildcard pistoseg_b200/csrc/*.cuh) include/pistoseg_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean

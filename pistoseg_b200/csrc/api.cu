@@ -1,0 +1,59 @@
+// Handle lifetime, error reporting, launch accounting for libpistoseg_b200 (C ABI: include/pistoseg_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pisto_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* pisto_last_error(void) { return g_err; }
+extern "C" int pisto_abi_version(void) { return PISTO_ABI_VERSION; }
+
+extern "C" int pisto_create(pisto_handle_t* out, int device) {
+  if (!out) { pisto_set_error("pisto_create: out is NULL"); return PISTO_ERR_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    pisto_set_error("pisto_create: no CUDA device visible (%s); libpistoseg_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
+    return PISTO_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { pisto_set_error("pisto_create: device %d out of range [0,%d)", device, n); return PISTO_ERR_INVALID; }
+  cudaDeviceProp p;
+  PISTO_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) {
+    pisto_set_error("pisto_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+    return PISTO_ERR_NO_DEVICE;
+  }
+  pisto_ctx* c = new pisto_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->sm_count = p.multiProcessorCount;
+  c->smem_optin = (int)p.sharedMemPerBlockOptin;
+  *out = c;
+  return PISTO_OK;
+}
+
+extern "C" int pisto_destroy(pisto_handle_t h) {
+  if (!h) return PISTO_OK;
+  if (h->pipe_ready) {
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 2; i++) {
+      if (h->pipe_dev[i]) cudaFree(h->pipe_dev[i]);
+      if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
+      if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
+    }
+  }
+  delete h;
+  return PISTO_OK;
+}
+
+extern "C" int64_t pisto_launch_count(pisto_handle_t h) { return h ? h->launches : 0; }
