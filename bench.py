@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- tiles/sec of the multi-scale + flip pseudo-mask fusion (BASELINE.json metric) on N B200s.
+
+One "step" = one pass of the fused hot path (pisto_fuse_argmax_confusion) over one batch of synthetic tiles of
+BASELINE config 2 (WSSS4LUAD pseudo-mask inference: 224x224 tiles, 3 classes, scales {0.75,1,1.25} x hflip = 6 stride-8
+views, class-presence vector, background mask, uint8 label map + 32x32 logit export).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            ours, one process per GPU (torchrun for N > 1)
+  python bench.py --impl reference ...                            the reference's own torch-CPU path (oracle/pipeline.py)
+
+Prints ONE JSON line on stdout (contract in the task statement); diagnostics go to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tiles/sec, multi-scale+flip pseudo-mask fusion"
+UNIT = "tiles/s"
+SCALES = (0.75, 1.0, 1.25)
+T, C = 224, 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def bytes_per_tile(sizes, with_gt=False):
+    """Algorithmic (compulsory) HBM bytes per tile, SURVEY.md 8(d): views + bg + label (+ gt) + 32x32 logits."""
+    return 4 * C * sum(h * h for h in sizes) + T * T * (2 + int(with_gt)) + 4 * C * 32 * 32
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.t = [], []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip()); self.t.append(time.time())
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        sel = [r for r, t in zip(self.rows, self.t) if t0 <= t <= t1 + 0.06] or self.rows[-3:]
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in sel:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(n_tiles, repeats=1):
+    """The reference's torch-CPU path on a bounded sample of the same workload, all host threads."""
+    from oracle import pipeline
+    from pistoseg_b200 import synthetic
+    torch.set_num_threads(os.cpu_count())
+    cfg = synthetic.cfg2(N=n_tiles, T=T, C=C, scales=SCALES)
+    pres, bg = cfg["present"].numpy(), cfg["bg"].numpy()
+    pipeline.pseudo_mask_batch([v[:8] for v in cfg["views"]], cfg["codes"], (T, T), pres[:8], bg[:8])  # warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        pipeline.pseudo_mask_batch(cfg["views"], cfg["codes"], (T, T), pres, bg)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_tiles / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: calibrate on 64 tiles, then size each step so that W + K steps take about args.cpu_budget seconds
+    rate, _ = cpu_reference_run(64)
+    n = int(max(32, min(args.cpu_tiles, args.cpu_budget * rate / (args.steps + args.warmup))))
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_reference_run(n)
+        if i >= args.warmup:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    val = n / dt
+    sizes = [int(T * s) // 8 for s in SCALES for _ in (0, 1)]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: WSSS4LUAD pseudo-mask inference, 224x224 tiles, C=3, scales {0.75,1,1.25} x hflip (V=6 stride-8 views 21/28/35), present vector (40% single-label), bg mask, u8 labels + 32x32 logits",
+                   "tiles_per_step": n, "views": sizes},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{n} tiles per step x {args.steps} steps; oracle/pipeline.py (literal torch-CPU restatement of infer_pseudo_masks.py:118-154, torch.set_num_threads({os.cpu_count()}))"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from pistoseg_b200 import _lib, ops, synthetic
+    from pistoseg_b200._lib import DECIDE_SOFTMAX, MASK_FILL
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pistoseg_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = args.tiles
+    sizes = synthetic.view_sizes(T, SCALES)
+    # synthetic inputs: a 1024-tile seeded block generated on the CPU (identical bits to what the oracle sees),
+    # tiled up to N on the device so that one step streams 2.8 GB (>> 126 MB L2) through the kernel
+    base = synthetic.cfg2(N=min(N, 1024), T=T, C=C, scales=SCALES)
+    rep = (N + base["views"][0].shape[0] - 1) // base["views"][0].shape[0]
+
+    def up(t):
+        return t.to(dev).repeat((rep,) + (1,) * (t.dim() - 1))[:N].contiguous()
+    views = [up(v) for v in base["views"]]
+    bg, present = up(base["bg"]), up(base["present"])
+    codes = base["codes"]
+
+    def step():
+        return ops.fuse_argmax_confusion(views, codes, (T, T), mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=present, bg=bg,
+                                         bg_match=1, bg_label=C, lowres=(32, 32))
+    out = step()
+    torch.cuda.synchronize()
+    if rank == 0 and not args.skip_check:
+        # cheap in-run sanity check against the oracle on the first 64 tiles (not timed)
+        from oracle import fuse as ofuse
+        sub = {k: [v[:64] for v in base["views"]] if k == "views" else base[k] for k in ("views", "codes")}
+        fused = ofuse.fuse_views(sub["views"], sub["codes"], (T, T))
+        lab = ofuse.pseudo_masks(fused, base["present"][:64].numpy(), base["bg"][:64].numpy())
+        agree = float((out["labels"][:64].cpu().numpy() == lab).mean())
+        assert agree >= 0.9999, f"label agreement with the oracle {agree}"
+        assert torch.equal(out["lowres"][:64].cpu(), ofuse.lowres_32(fused)), "32x32 logits differ from the oracle"
+        log(f"parity check on 64 tiles: label agreement {agree:.6f}, 32x32 logits bit-exact")
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count(local)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.launch_count(local) - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- end to end: host (pinned) buffers through the C ABI's *_host call, H2D + kernel + D2H inside the timed region
+    Ne = args.e2e_tiles
+    repe = (Ne + base["views"][0].shape[0] - 1) // base["views"][0].shape[0]
+
+    def pin(t):
+        return t.repeat((repe,) + (1,) * (t.dim() - 1))[:Ne].contiguous().pin_memory()
+    hviews = [pin(v) for v in base["views"]]
+    hbg, hpres = pin(base["bg"]), pin(base["present"])
+    hout = {"labels": torch.empty((Ne, T, T), dtype=torch.uint8).pin_memory(), "lowres": torch.empty((Ne, C, 32, 32), dtype=torch.float32).pin_memory()}
+
+    def estep():
+        ops.fuse_argmax_confusion_host(hviews, codes, (T, T), mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=hpres, bg=hbg, bg_match=1,
+                                       bg_label=C, lowres=(32, 32), chunk=args.e2e_chunk, device=local, out=hout)
+        return _lib.last_pipeline_ms(local)
+    for _ in range(2):
+        estep()
+    if world > 1:
+        dist.barrier()
+    e_ms = 0.0
+    for _ in range(args.e2e_steps):
+        e_ms += estep()
+    if world > 1:
+        t = torch.tensor([e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    assert torch.equal(hout["labels"][:256], out["labels"][:256].cpu()), "e2e labels differ from the device-resident run"
+    h2d = sum(v[0].numel() * 4 for v in hviews) * Ne + hbg[0].numel() * Ne + C * Ne
+    d2h = (T * T + C * 32 * 32 * 4) * Ne
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    value = world * N * args.steps / (ms * 1e-3)
+    bpt = bytes_per_tile(sizes)
+    peak, peak_src = measured_peak()
+    per_launch_ms = ms / max(launches, 1)
+    achieved = bpt * N / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("tiles_per_launch"):
+            traffic = tj["dram_bytes_per_launch"] * (N / tj["tiles_per_launch"])
+    except Exception:
+        pass
+    fp32_instr_per_tile = T * T * C * len(sizes) * 3  # mul + fma + add per (pixel, class, view): the exact-order lower bound
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: WSSS4LUAD pseudo-mask inference, 224x224 tiles, C=3, scales {0.75,1,1.25} x hflip (V=6 stride-8 views 21/28/35), present vector (40% single-label), bg mask, u8 labels + 32x32 logits",
+                   "tiles_per_step_per_gpu": N, "views": sizes, "parallelism": f"tile-sharded x{world}, no data-path collective",
+                   "l2": f"inputs+outputs {bpt * N / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_tile": bpt, "kernel": "fuse_stream_kernel<3,6,2>",
+                     "note": "kernel is FP32-issue-bound, not HBM-bound (DESIGN.md): fp32_frac = exact-order FP32 instr / (148 SM x 128 lanes x sm clock)",
+                     "fp32_frac": fp32_instr_per_tile * N / (per_launch_ms * 1e-3) / (148 * 128 * (clocks["sm_mhz"] if clocks else 1965.0) * 1e6)},
+        "e2e": {"value": world * Ne * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "tiles_per_step_per_gpu": Ne, "api": "pistoseg_b200.ops.fuse_argmax_confusion_host -> pisto_fuse_argmax_confusion_host (pinned host buffers)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_reference_run(args.cpu_tiles)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{args.cpu_tiles} tiles of the same workload, oracle/pipeline.py (torch-CPU restatement of infer_pseudo_masks.py:118-154), {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=16384, help="tiles per step per GPU")
+    ap.add_argument("--e2e-tiles", type=int, default=8192)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunk", type=int, default=1024)
+    ap.add_argument("--cpu-tiles", type=int, default=1536, help="bounded CPU sample")
+    ap.add_argument("--cpu-budget", type=float, default=90.0, help="seconds of CPU work for the whole --impl reference run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-check", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

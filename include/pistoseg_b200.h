@@ -132,6 +132,8 @@ int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t* views_host
  * This is the call the end-to-end ("e2e") benchmark times.  conf_host is int64[C*C], accumulated. */
 int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_view_t* views_host_ptrs, int V,
                                      const pisto_fuse_args_t* args_host_ptrs, int chunk);
+/* device-clock duration (CUDA events, first H2D start -> last D2H end) of the last *_host call on this handle */
+double pisto_last_pipeline_ms(pisto_handle_t h);
 
 /* -------------------------------------------------------------------------------------------------- */
 /* bilinear resize, align_corners=False: replaces interpolate_tensor / F.interpolate(mode='bilinear') */

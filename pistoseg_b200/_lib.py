@@ -66,6 +66,7 @@ SYMBOLS = {
     "pisto_confusion_accumulate": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "pisto_fuse_argmax_confusion": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _vp]),
     "pisto_fuse_argmax_confusion_host": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _i]),
+    "pisto_last_pipeline_ms": (_d, [_vp]),
     "pisto_upsample_bilinear": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "pisto_stitch_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "pisto_canvas_normalize": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
@@ -120,3 +121,8 @@ def handle(device_index):
 def launch_count(device_index=0):
     h = _handles.get(device_index)
     return int(load().pisto_launch_count(h)) if h is not None else 0
+
+
+def last_pipeline_ms(device_index=0):
+    h = _handles.get(device_index)
+    return float(load().pisto_last_pipeline_ms(h)) if h is not None else 0.0

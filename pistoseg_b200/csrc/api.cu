@@ -49,8 +49,10 @@ extern "C" int pisto_destroy(pisto_handle_t h) {
     for (int i = 0; i < 2; i++) {
       if (h->pipe_dev[i]) cudaFree(h->pipe_dev[i]);
       if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
+      if (h->pipe_t1[i]) cudaEventDestroy(h->pipe_t1[i]);
       if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
+    if (h->pipe_t0) cudaEventDestroy(h->pipe_t0);
   }
   delete h;
   return PISTO_OK;

@@ -26,6 +26,8 @@ struct pisto_ctx {
   cudaEvent_t pipe_done[2];
   void* pipe_dev[2];
   size_t pipe_dev_bytes[2];
+  cudaEvent_t pipe_t0, pipe_t1[2];  // timing of the last host-buffer call (device clock)
+  float pipe_last_ms;
   bool pipe_ready;
 };
 

@@ -18,7 +18,9 @@ int ensure_pipe(pisto_ctx* h, size_t bytes) {
     for (int i = 0; i < 2; i++) {
       PISTO_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking));
       PISTO_CUDA(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
+      PISTO_CUDA(cudaEventCreate(&h->pipe_t1[i]));
     }
+    PISTO_CUDA(cudaEventCreate(&h->pipe_t0));
     h->pipe_ready = true;
   }
   for (int i = 0; i < 2; i++) {
@@ -66,6 +68,9 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
   int rc = ensure_pipe(h, off);
   if (rc != PISTO_OK) return rc;
 
+  // device-clock timing of the whole call: t0 on stream 0 (stream 1 waits for it), one end event per stream
+  PISTO_CUDA(cudaEventRecord(h->pipe_t0, h->pipe_stream[0]));
+  PISTO_CUDA(cudaStreamWaitEvent(h->pipe_stream[1], h->pipe_t0, 0));
   if (a->conf) for (int s = 0; s < 2; s++) PISTO_CUDA(cudaMemsetAsync((char*)h->pipe_dev[s] + o_conf, 0, (size_t)C * C * sizeof(unsigned long long), h->pipe_stream[s]));
 
   int k = 0;
@@ -101,8 +106,17 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
   unsigned long long part[2][PISTO_MAX_CLASSES * PISTO_MAX_CLASSES];
   for (int s = 0; s < 2; s++) {
     if (a->conf) PISTO_CUDA(cudaMemcpyAsync(part[s], (char*)h->pipe_dev[s] + o_conf, (size_t)C * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->pipe_stream[s]));
+    PISTO_CUDA(cudaEventRecord(h->pipe_t1[s], h->pipe_stream[s]));
     PISTO_CUDA(cudaStreamSynchronize(h->pipe_stream[s]));
+  }
+  {
+    float m0 = 0.f, m1 = 0.f;
+    PISTO_CUDA(cudaEventElapsedTime(&m0, h->pipe_t0, h->pipe_t1[0]));
+    PISTO_CUDA(cudaEventElapsedTime(&m1, h->pipe_t0, h->pipe_t1[1]));
+    h->pipe_last_ms = m0 > m1 ? m0 : m1;
   }
   if (a->conf) for (int i = 0; i < C * C; i++) a->conf[i] += part[0][i] + part[1][i];
   return PISTO_OK;
 }
+
+extern "C" double pisto_last_pipeline_ms(pisto_handle_t h) { return h ? (double)h->pipe_last_ms : 0.0; }

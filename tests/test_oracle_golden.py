@@ -1,0 +1,125 @@
+"""The CPU oracle against fixtures produced by the reference's own code (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bilinear as obil
+from oracle import confusion as oconf
+from oracle import fuse as ofuse
+from oracle import mosaic as omosaic
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name))
+
+
+@pytest.mark.parametrize("tag,C", [("luad", 3), ("bcss", 4), ("empty", 3)])
+def test_confusion_and_iou_match_reference_loss_py(tag, C):
+    z = load("miou.npz")
+    l1, l2 = torch.from_numpy(z[f"{tag}_logits1"]), torch.from_numpy(z[f"{tag}_logits2"])
+    cm = oconf.generate_matrix(ofuse.miou_pred(l1).numpy(), z[f"{tag}_mask1"], C)
+    ret1 = (oconf.mean_iou(cm), oconf.fw_iou(cm))
+    assert np.array_equal(np.array(ret1), z[f"{tag}_ret1"])
+    cm = cm + oconf.generate_matrix(ofuse.miou_pred(torch.softmax(l2, 1), probs=True).numpy(), z[f"{tag}_mask2"], C)
+    assert np.array_equal(cm.astype(np.float64), z[f"{tag}_cm"])
+    assert np.array_equal(oconf.tissue_iou(cm), z[f"{tag}_tissue"])
+    assert oconf.mean_iou(cm) == float(z[f"{tag}_miou"])
+    assert oconf.fw_iou(cm) == float(z[f"{tag}_fwiou"])
+    assert np.array_equal(np.array([oconf.mean_iou(cm), oconf.fw_iou(cm)]), z[f"{tag}_ret2"])
+
+
+def test_empty_class_iou_is_zero_and_skipped_in_fwiou():
+    z = load("miou.npz")
+    assert z["empty_tissue"][2] == 0.0
+    assert z["empty_cm"][2].sum() == 0 and z["empty_cm"][:, 2].sum() == 0
+
+
+def test_get_mask_pred_and_entropy_matches_reference_function():
+    z = load("pmask.npz")
+    i = 0
+    while f"logit{i}" in z:
+        logit = torch.from_numpy(z[f"logit{i}"].copy())
+        lab = [int(v) for v in z[f"label{i}"]]
+        mask, ent = ofuse.get_mask_pred_and_entropy(logit, z[f"tissue{i}"], lab)
+        assert np.array_equal(np.asarray(mask), z[f"mask{i}"]), i
+        assert np.array_equal(np.asarray(ent, dtype=np.float32), z[f"entropy{i}"]), i
+        assert np.array_equal(logit.numpy(), z[f"mutated{i}"]), "in-place -1e10 fill must be visible to the caller"
+        # batch driver (what the GPU tests use) == per-tile reference function
+        fused = torch.from_numpy(z[f"logit{i}"].copy())[None]
+        got = ofuse.pseudo_masks(fused, np.array([lab]), (z[f"tissue{i}"] == 0)[None])
+        assert np.array_equal(got[0], z[f"mask{i}"].astype(np.uint8))
+        # 56 -> 8 export is the gather [3::7, 3::7]
+        assert np.array_equal(z[f"low{i}"], z[f"logit{i}"][:, 3::7, 3::7])
+        assert np.array_equal(obil.bilinear_restated(z[f"logit{i}"], (8, 8)), z[f"low{i}"])
+        i += 1
+    assert i == 7
+
+
+def test_bilinear_restatement_matches_torch_interpolate():
+    z = load("bilinear.npz")
+    for i in range(int(z["n"])):
+        x, y, size = z[f"x{i}"], z[f"y{i}"], tuple(int(v) for v in z[f"size{i}"])
+        got = obil.bilinear_restated(x, size)
+        assert got.dtype == y.dtype
+        # fixtures were produced by ATen's vectorised CPU kernel (and equal the CUDA kernel, profiles/r01/probe_torch.json)
+        assert np.array_equal(got, y), (i, np.abs(got - y).max())
+
+
+def test_bilinear_restatement_within_gate_of_live_torch():
+    """Whatever code path this machine's torch takes (it depends on shape / thread count), the restatement stays within
+    the 1e-5 float gate of it (in fact within 2 ulp)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    for shp, size in (((1, 3, 8, 8), (16, 16)), ((1, 3, 3, 5), (7, 11)), ((1, 3, 256, 256), (32, 32)), ((2, 3, 28, 28), (224, 224))):
+        x = torch.randn(shp, generator=g) * 3
+        ref = F.interpolate(x, size, mode="bilinear").numpy()
+        got = obil.bilinear_restated(x.numpy(), size)
+        assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1)).max() <= 1e-6
+
+
+def _plan_from_row(row, Ms):
+    quads = []
+    for q in range(4):
+        flip, warp, cy, cx = (int(v) for v in row[2 + 4 * q: 6 + 4 * q])
+        quads.append(dict(flip=flip, warp=bool(warp), crop_y=cy, crop_x=cx, M=Ms[q] if warp else None))
+    return dict(split_h=int(row[0]), split_w=int(row[1]), quads=quads)
+
+
+def unpack_pool(z, tag):
+    hw = z[f"{tag}_pool_hw"]
+    flat = z[f"{tag}_pool"]
+    bgflat = z[f"{tag}_bg"] if f"{tag}_bg" in z else None
+    pool, bgs, o = [], [], 0
+    for h, w in hw:
+        pool.append(flat[3 * o: 3 * (o + h * w)].reshape(h, w, 3))
+        if bgflat is not None:
+            bgs.append(bgflat[o: o + h * w].reshape(h, w))
+        o += h * w
+    return pool, (bgs if bgflat is not None else None)
+
+
+@pytest.mark.parametrize("tag,pn,ps", [("luad", 4, 16), ("bcss", 2, 32)])
+def test_mosaic_oracle_matches_cv2_fixtures(tag, pn, ps):
+    z = load("mosaic.npz")
+    pool, bgs = unpack_pool(z, tag)
+    for t in range(z[f"{tag}_img"].shape[0]):
+        plan = _plan_from_row(z[f"{tag}_plan"][t], z[f"{tag}_M{t}"])
+        img, msk = omosaic.synthesize(plan, z[f"{tag}_cells"][t], pool, bgs, z[f"{tag}_labels"], pn, ps, use_cv2=False)
+        assert np.array_equal(img, z[f"{tag}_img"][t]), t
+        assert np.array_equal(msk, z[f"{tag}_mask"][t]), t
+
+
+def test_warp_affine_restatement_matches_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import warp_affine as wa
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        S = int(rng.choice([64, 96, 224]))
+        img = rng.integers(0, 256, (S, S, 3), dtype=np.uint8); msk = rng.integers(0, 4, (S, S), dtype=np.uint8)
+        M = wa.shift_scale_rotate_matrix(S, S, rng.uniform(-45, 45), rng.uniform(0.8, 1.2), rng.uniform(-.0625, .0625), rng.uniform(-.0625, .0625))
+        assert np.array_equal(wa.warp_affine_u8(img, M), cv2.warpAffine(img, M, (S, S), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101))
+        assert np.array_equal(wa.warp_affine_u8(msk, M, nearest=True), cv2.warpAffine(msk, M, (S, S), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_REFLECT_101))
