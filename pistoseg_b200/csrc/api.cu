@@ -38,12 +38,19 @@ extern "C" int pisto_create(pisto_handle_t* out, int device) {
   c->device = device;
   c->sm_count = p.multiProcessorCount;
   c->smem_optin = (int)p.sharedMemPerBlockOptin;
+  PISTO_CUDA(cudaSetDevice(device));
+  if (cudaMalloc(&c->sched, PISTO_SCHED_SLOTS * sizeof(int)) != cudaSuccess) {
+    delete c;
+    pisto_set_error("pisto_create: cudaMalloc failed");
+    return PISTO_ERR_CUDA;
+  }
   *out = c;
   return PISTO_OK;
 }
 
 extern "C" int pisto_destroy(pisto_handle_t h) {
   if (!h) return PISTO_OK;
+  if (h->sched) { cudaSetDevice(h->device); cudaFree(h->sched); }
   if (h->pipe_ready) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 2; i++) {

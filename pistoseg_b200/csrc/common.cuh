@@ -15,12 +15,15 @@
 
 #define PISTO_MAX_VIEWS 16
 #define PISTO_MAX_CLASSES 8
+#define PISTO_SCHED_SLOTS 256
 
 struct pisto_ctx {
   int device;
   int sm_count;
   int smem_optin;   // max dynamic shared memory per block
   long long launches;
+  int* sched;       // ring of device tile counters for the persistent kernels' dynamic scheduler
+  unsigned int sched_next;
   // resources of the host-buffer (e2e) pipeline, created lazily
   cudaStream_t pipe_stream[2];
   cudaEvent_t pipe_done[2];

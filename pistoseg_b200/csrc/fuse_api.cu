@@ -76,6 +76,10 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
   if (a->impl != 1) {
     rc = pisto_launch_fuse_stream(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
+    if (!launched) {
+      rc = pisto_launch_fuse_block(h, p, st, &launched);
+      if (rc != PISTO_OK) return rc;
+    }
     if (!launched && a->impl == 2) {
       pisto_set_error("pisto_fuse_argmax_confusion: impl=2 (streaming kernel) has no instantiation for C=%d V=%d T=%dx%d with these options",
                       p.C, p.V, p.T_h, p.T_w);

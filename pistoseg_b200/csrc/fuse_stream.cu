@@ -1,442 +1,484 @@
-// Streaming fusion kernel -- the hot path of the library (BASELINE configs 1, 2, 3, 5).
+// Streaming fusion kernel -- the hot path of the library for tiles whose views fit in shared memory whole
+// (BASELINE configs 1, 2, 3: 224-px tiles, stride-8 multi-scale logits).
 //
-// Work item = (tile n, output block by x bx).  A CTA walks its items persistently:
-//   A. per view, the raw (augmented-frame) sub-rectangle of low-resolution logits that the block needs is staged in
-//      shared memory (whole views for 224-px tiles: 58.8 KB for cfg 2);  de-augmentation (flip / rot90) is NOT
-//      materialised -- it is an affine index map applied when the staged values are read;
-//   B. two small tables are built in shared memory: per (view, output row) the vertical lerp weights + the shared-
-//      memory row offsets of the two source rows (+ a 2-bit "advance" flag hidden in the weights' sign bits), and per
-//      (view, output column) the horizontal lerp weights + column offsets;
-//   C. every thread owns COLS adjacent output columns and streams down a strip of rows.  For each view it keeps, in
-//      registers, the HORIZONTALLY interpolated values of the two source rows that bracket the current output row
-//      (Ha, Hb: 2*C*COLS registers per view).  Per output row and view the work is then exactly
-//          t = l1*Hb;  o = fma(l0, Ha, t);  acc = acc + o            (3 FP32 ops per class and pixel)
-//      and only when the source-row pair advances (every ~8 rows for stride-8 logits) two shared-memory reads and
-//      one fma per value refresh Hb.  This is the separable form of torch's
-//          fma(h0, fma(w0,a, w1*b), h1 * fma(w0,c, w1*d))
-//      with identical association, hence bit-identical results at ~3.4 instead of ~12 instructions
-//      per (pixel, class, view).
-//   D. per pixel: mask / argmax (pisto_decide: margin fast path, exact slow path), confusion counters packed in two
-//      64-bit registers, background overwrite, 2-byte label store, optional fused-score / 32x32 logit export.
+// One persistent CTA per SM; tiles are claimed from a global atomic counter (single-label tiles are ~20x cheaper
+// than multi-label ones, so static assignment would leave SMs idle).
 //
-// The kernel is FP32-issue-bound for V >= 2 (see DESIGN.md "Roofline"); HBM traffic is the compulsory minimum
-// (every input byte is read once, every output byte written once).
+//   TMA pipeline   Every view of a tile is ONE contiguous run of C*h*w floats in HBM.  Thread 0 fetches the runs of
+//                  the NEXT tile with cp.async.bulk (1-D TMA, mbarrier complete_tx) into the other half of a double
+//                  buffer while all warps compute the current tile.  Runs are not 16-byte multiples (21*21*3 floats),
+//                  so the enclosing 16-byte-aligned span is copied and the 0..3-float shift is folded into the shared
+//                  memory base when the values are read.  De-augmentation (flip / rot90) is an affine index map on the
+//                  staged raw view -- never materialised.
+//   tables         Built once per launch (whole-tile geometry is the same for every tile): per (view, row) the
+//                  vertical lerp weights, pre-duplicated {l0,l0,l1,l1} so one 128-bit shared load yields both packed
+//                  operands; per row a 2-bit-per-view "source rows moved" word; per (view, col) the horizontal lerp
+//                  weights and column offsets.
+//   arithmetic     A thread owns 2 adjacent output columns and streams down a strip of rows, keeping for every view
+//                  the horizontally interpolated values of the two bracketing source rows in registers (Ha, Hb), both
+//                  columns PACKED in one 64-bit register.  Per (row, view, class) the work is three packed
+//                  instructions  t = mul.f32x2(l1, Hb); o = fma.f32x2(l0, Ha, t); acc = add.f32x2(acc, o)
+//                  -- the separable form of torch's fma(h0, fma(w0,a,w1*b), h1*fma(w0,c,w1*d)) with identical
+//                  association and rounding (bit-exact).  FFMA2/FMUL2/FADD2 occupy the FP32 pipe for
+//                  two cycles but take one issue slot (profiles/r01/probe_microbench.txt), which leaves the other
+//                  slot for the table loads / branches / integer work of the loop.
+//   epilogue       mask / argmax (margin fast path, exact slow path: common.cuh), confusion counters packed in two
+//                  64-bit registers, background overwrite, 2-byte label store, 32x32 logit gather.
+//
+// Roofline: FP32-pipe-bound for V >= 2 (3*C*V packed-lane operations per pixel); HBM traffic is the compulsory
+// minimum (each input byte read once by TMA, each output byte written once).
 #include "fuse_common.cuh"
 
 namespace {
 
-constexpr int kMaxThreads = 448;
+constexpr int kMaxThreads = 384;
+typedef unsigned long long u64;
 
-struct SubRect {
-  int a_lo, b_lo, nrows, pitch;
-  int base2, si2, sj2, plane;
-};
+// ---- packed f32x2 arithmetic (sm_100+) -----------------------------------------------------------------------
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// ---- mbarrier / 1-D TMA ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a lost TMA must surface as a launch failure, never as a hung GPU
+#pragma unroll 1
+  for (int it = 0; it < (1 << 26); it++)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct StreamGeom {
-  int BW, BH, nbx, nby;
-  int GX, S, rows_per_strip;
-  int view_off[PISTO_MAX_VIEWS];  // float offset of each view's staging area
-  int view_cap[PISTO_MAX_VIEWS];  // floats
-  int sr_off, rowtab_off, coltab_off, views_off, hist_off;  // byte offsets into dynamic smem
+  int GX, S, rows_per_strip, threads;
+  int view_off[PISTO_MAX_VIEWS];  // float offset of each view inside one staging buffer (16-byte aligned)
+  int view_plane[PISTO_MAX_VIEWS];
+  int buf_floats;                 // floats per staging buffer
+  int ctl_off, flags_off, rowoff_off, rowtab_off, coltab_off, views_off;  // byte offsets into dynamic smem
   int smem_bytes;
-  long long n_items;
+  int* counter;                   // global tile counter (zeroed before the launch)
 };
 
-__device__ __forceinline__ void minmax2(int u, int v, int& lo, int& hi) { lo = u < v ? u : v; hi = u < v ? v : u; }
+struct Ctl {
+  uint64_t mbar[2];
+  int tile[2];
+  unsigned int hist[64];
+};
 
-template <int C, int V, int COLS>
+// first index of the maximum, the maximum and the runner-up of v[0..C)
+template <int C>
+__device__ __forceinline__ void top2(const float (&v)[C], int& bi, float& bv, float& sv) {
+  bi = 0; bv = v[0]; sv = -INFINITY;
+#pragma unroll
+  for (int c = 1; c < C; c++) {
+    const bool gt = v[c] > bv;
+    sv = fmaxf(sv, fminf(bv, v[c]));
+    bi = gt ? c : bi;
+    bv = fmaxf(bv, v[c]);
+  }
+}
+
+// Label of one pixel from the undivided view sums a[] (see pisto_decide in common.cuh for the proof sketch of the
+// fast path); madd[c] is 0 for usable classes and -inf for classes masked out by the tile's presence vector.
+template <int C>
+__device__ __forceinline__ int decide_px(const float (&a)[C], const float (&madd)[C], uint32_t present_bits, const DecideCfg& cfg,
+                                         bool fast_ok) {
+  float v[C];
+  float chk = a[0];
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    v[c] = __fadd_rn(a[c], madd[c]);
+    if (c) chk = __fadd_rn(chk, a[c]);
+  }
+  int bi; float bv, sv;
+  top2<C>(v, bi, bv, sv);
+  const float margin = __fmaf_rn(fabsf(bv), 2.4e-7f, cfg.margin_abs);
+  const bool ok = fast_ok && (__fsub_rn(bv, sv) > margin) && (fabsf(chk) < 1e30f) && (bv > -1e9f);
+  if (ok) return bi;
+  return pisto_decide<C>(a, present_bits, cfg, false, nullptr);
+}
+
+template <int C, int V, bool PROB>
 __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __grid_constant__ FuseParams p,
                                                                      const __grid_constant__ StreamGeom g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SubRect* sr = reinterpret_cast<SubRect*>(smem_raw + g.sr_off);
-  float4* rowtab = reinterpret_cast<float4*>(smem_raw + g.rowtab_off);  // [V][BH]
-  float4* coltab = reinterpret_cast<float4*>(smem_raw + g.coltab_off);  // [V][BW]
-  float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);
-  unsigned int* hist = reinterpret_cast<unsigned int*>(smem_raw + g.hist_off);  // [C*C]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem_raw + g.ctl_off);
+  unsigned int* rowflags = reinterpret_cast<unsigned int*>(smem_raw + g.flags_off);  // [T_h]
+  int2* rowoff = reinterpret_cast<int2*>(smem_raw + g.rowoff_off);                   // [V][T_h]
+  float4* rowtab = reinterpret_cast<float4*>(smem_raw + g.rowtab_off);               // [V][T_h] {l0,l0,l1,l1}
+  float4* coltab = reinterpret_cast<float4*>(smem_raw + g.coltab_off);               // [V][T_w] {oa,ob,l0,l1}
+  float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);                     // 2 staging buffers
 
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int T_h = p.T_h, T_w = p.T_w;
   const bool do_conf = p.conf != nullptr && p.gt != nullptr;
+  const bool need_low = p.lowres_out != nullptr && p.low_fh > 0;
   constexpr int BINS = C * C;
-  if (do_conf) {
-    for (int i = tid; i < BINS; i += nt) hist[i] = 0;
+
+  // ---- one-time setup: barriers, tables ---------------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(&ctl->mbar[0], 1);
+    mbar_init(&ctl->mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < 64; i += nt) ctl->hist[i] = 0;
+  for (int i = tid; i < V * T_h; i += nt) {
+    const int v = i / T_h, y = i - v * T_h;
+    const ViewDev& vw = p.view[v];
+    const int si2 = vw.map.ai * vw.w + vw.map.bi, base2 = vw.map.a0 * vw.w + vw.map.b0;
+    const Lerp L = pisto_src_index(vw.scale_h, y, vw.map.ho, vw.same_h);
+    rowtab[i] = make_float4(L.l0, L.l0, L.l1, L.l1);
+    rowoff[i] = make_int2(base2 + L.i0 * si2, base2 + L.i1 * si2);
+  }
+  for (int y = tid; y < T_h; y += nt) {
+    unsigned int f = 0;
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      unsigned int fl = 2;  // first row of a strip: load both source rows
+      if (y % g.rows_per_strip != 0) {
+        const Lerp L = pisto_src_index(vw.scale_h, y, vw.map.ho, vw.same_h);
+        const Lerp P = pisto_src_index(vw.scale_h, y - 1, vw.map.ho, vw.same_h);
+        fl = (P.i0 == L.i0 && P.i1 == L.i1) ? 0u : ((L.i0 == P.i1 && P.i1 == P.i0 + 1) ? 1u : 2u);
+      }
+      f |= fl << (2 * v);
+    }
+    rowflags[y] = f;
+  }
+  for (int i = tid; i < V * T_w; i += nt) {
+    const int v = i / T_w, x = i - v * T_w;
+    const ViewDev& vw = p.view[v];
+    const int sj2 = vw.map.aj * vw.w + vw.map.bj;
+    const Lerp L = pisto_src_index(vw.scale_w, x, vw.map.wo, vw.same_w);
+    coltab[i] = make_float4(__int_as_float(L.i0 * sj2), __int_as_float(L.i1 * sj2), L.l0, L.l1);
+  }
+
+  // does tile n read its views at all?  (single-label tiles without any score export do not)
+  auto tile_needs_views = [&](int n) -> bool {
+    if (p.fused_out || need_low) return true;
+    return pisto_tile_presence(p, n).single < 0;
+  };
+  // thread 0: fetch every view of tile n into staging buffer b
+  auto issue_tile = [&](int n, int b) {
+    float* buf = vsm + b * g.buf_floats;
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      const char* start = reinterpret_cast<const char*>(vw.logits + (long long)n * vw.tile_stride);
+      const char* end = start + (size_t)C * vw.h * vw.w * sizeof(float);
+      const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15);
+      const char* a1 = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(end) + 15) & ~(uintptr_t)15);
+      char* dst = reinterpret_cast<char*>(buf + g.view_off[v]);
+      if (n == p.N - 1) {
+        // never read past the end of the caller's buffer: copy whole 16-byte units only, the (<16-byte) tail by hand
+        a1 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(end) & ~(uintptr_t)15);
+        if (a1 < a0) a1 = a0;
+        const char* t = a1 > start ? a1 : start;
+        for (; t < end; t += 4) *reinterpret_cast<float*>(dst + (t - a0)) = *reinterpret_cast<const float*>(t);
+      }
+      const uint32_t bytes = (uint32_t)(a1 - a0);
+      if (bytes) bulk_g2s(dst, a0, bytes, &ctl->mbar[b]);
+      total += bytes;
+    }
+    mbar_arrive_expect_tx(&ctl->mbar[b], total);
+  };
+
+  if (tid == 0) {
+    const int t0 = atomicAdd(g.counter, 1);
+    ctl->tile[0] = t0 < p.N ? t0 : -1;
+    if (t0 < p.N && tile_needs_views(t0)) issue_tile(t0, 0);
+  }
+  __syncthreads();
+
   const bool worker = tid < g.GX * g.S;
   const int grp = tid % g.GX, strip = tid / g.GX;
-  const int xl0 = grp * COLS;
+  const int x = 2 * grp;
+  const int ys = strip * g.rows_per_strip;
+  const int ye = min(ys + g.rows_per_strip, T_h);
+  // which of my two columns (if any) is a 32x32 gather column
+  int lowcol_mask = 0;
+  if (need_low) {
+    if (x % p.low_fw == p.low_fw / 2) lowcol_mask |= 1;
+    if ((x + 1) % p.low_fw == p.low_fw / 2) lowcol_mask |= 2;
+  }
+  unsigned int uses0 = 0, uses1 = 0;  // completed phases of the two barriers
 
-  for (long long item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-    const int bx = (int)(item % g.nbx);
-    const int by = (int)((item / g.nbx) % g.nby);
-    const int n = (int)(item / ((long long)g.nbx * g.nby));
-    const int y0 = by * g.BH, x0 = bx * g.BW;
-    const int bh = min(g.BH, p.T_h - y0), bw = min(g.BW, p.T_w - x0);
+  for (int k = 0;; k++) {
+    const int b = k & 1;
+    const int n = ctl->tile[b];
+    if (n < 0) break;
+    if (tid == 0) {
+      const int t1 = atomicAdd(g.counter, 1);
+      ctl->tile[b ^ 1] = t1 < p.N ? t1 : -1;
+      if (t1 < p.N && tile_needs_views(t1)) issue_tile(t1, b ^ 1);
+    }
     const TilePresence tp = pisto_tile_presence(p, n);
     const bool need_scores = tp.single < 0 || p.fused_out != nullptr;
-    const bool need_low = p.lowres_out != nullptr && p.low_fh > 0;
-
-    __syncthreads();  // previous item's readers are done with the staging area / tables
-    if (need_scores || need_low) {
-      // ---- A. sub-rectangles ---------------------------------------------------------------------------------
-      if (tid < V) {
-        const ViewDev& vw = p.view[tid];
-        const ViewMap& m = vw.map;
-        int r_lo = pisto_src_index(vw.scale_h, y0, m.ho, vw.same_h).i0;
-        int r_hi = pisto_src_index(vw.scale_h, y0 + bh - 1, m.ho, vw.same_h).i1;
-        int c_lo = pisto_src_index(vw.scale_w, x0, m.wo, vw.same_w).i0;
-        int c_hi = pisto_src_index(vw.scale_w, x0 + bw - 1, m.wo, vw.same_w).i1;
-        int l1, h1, l2, h2;
-        minmax2(m.ai * r_lo, m.ai * r_hi, l1, h1);
-        minmax2(m.aj * c_lo, m.aj * c_hi, l2, h2);
-        int a_lo = m.a0 + l1 + l2, a_hi = m.a0 + h1 + h2;
-        minmax2(m.bi * r_lo, m.bi * r_hi, l1, h1);
-        minmax2(m.bj * c_lo, m.bj * c_hi, l2, h2);
-        int b_lo = m.b0 + l1 + l2, b_hi = m.b0 + h1 + h2;
-        SubRect s;
-        s.a_lo = a_lo; s.b_lo = b_lo; s.nrows = a_hi - a_lo + 1; s.pitch = b_hi - b_lo + 1;
-        s.plane = s.nrows * s.pitch;
-        s.base2 = (m.a0 - a_lo) * s.pitch + (m.b0 - b_lo);
-        s.si2 = m.ai * s.pitch + m.bi;
-        s.sj2 = m.aj * s.pitch + m.bj;
-        if (C * s.plane > g.view_cap[tid]) __trap();  // host geometry and device geometry disagree: never expected
-        sr[tid] = s;
-      }
-      __syncthreads();
-      // ---- B. staging + tables -------------------------------------------------------------------------------
-#pragma unroll 1
-      for (int v = 0; v < V; v++) {
-        const ViewDev& vw = p.view[v];
-        const SubRect s = sr[v];
-        const float* src = vw.logits + (long long)n * vw.tile_stride;
-        float* dst = vsm + g.view_off[v];
-        if (s.pitch == vw.w) {
-          // full-width rows: each class plane is one contiguous run (the whole view when nrows == h)
-          const int run = s.plane;
-          for (int c = 0; c < C; c++) {
-            const float* sp = src + (long long)c * vw.h * vw.w + s.a_lo * vw.w;
-            float* dp = dst + c * run;
-#pragma unroll 4
-            for (int i = tid; i < run; i += nt) dp[i] = __ldg(sp + i);
-          }
-        } else {
-          const int rows = C * s.nrows;
-          for (int r = tid / 32; r < rows; r += nt / 32) {
-            int c = r / s.nrows, a = r - c * s.nrows;
-            const float* sp = src + (long long)c * vw.h * vw.w + (long long)(s.a_lo + a) * vw.w + s.b_lo;
-            float* dp = dst + r * s.pitch;
-            for (int b = tid & 31; b < s.pitch; b += 32) dp[b] = __ldg(sp + b);
-          }
-        }
-      }
-      for (int i = tid; i < V * bh; i += nt) {
-        int v = i / bh, yl = i - v * bh;
-        const ViewDev& vw = p.view[v];
-        const SubRect s = sr[v];
-        Lerp L = pisto_src_index(vw.scale_h, y0 + yl, vw.map.ho, vw.same_h);
-        int flag = 0;
-        if (yl % g.rows_per_strip != 0) {
-          Lerp P = pisto_src_index(vw.scale_h, y0 + yl - 1, vw.map.ho, vw.same_h);
-          if (P.i0 != L.i0 || P.i1 != L.i1) flag = (L.i0 == P.i1 && P.i1 == P.i0 + 1) ? 1 : 2;
-        }
-        float4 e;
-        e.x = __int_as_float(__float_as_int(L.l0) | ((flag & 1) << 31));
-        e.y = __int_as_float(__float_as_int(L.l1) | ((flag >> 1) << 31));
-        e.z = __int_as_float(s.base2 + L.i0 * s.si2);
-        e.w = __int_as_float(s.base2 + L.i1 * s.si2);
-        rowtab[v * g.BH + yl] = e;
-      }
-      for (int i = tid; i < V * bw; i += nt) {
-        int v = i / bw, xl = i - v * bw;
-        const ViewDev& vw = p.view[v];
-        const SubRect s = sr[v];
-        Lerp L = pisto_src_index(vw.scale_w, x0 + xl, vw.map.wo, vw.same_w);
-        float4 e;
-        e.x = __int_as_float(L.i0 * s.sj2);
-        e.y = __int_as_float(L.i1 * s.sj2);
-        e.z = L.l0;
-        e.w = L.l1;
-        coltab[v * g.BW + xl] = e;
-      }
+    const bool staged = need_scores || need_low;
+    if (staged) {
+      const unsigned int ph = b ? uses1 : uses0;
+      mbar_wait(&ctl->mbar[b], ph & 1u);
+      if (b) uses1++; else uses0++;
     }
-    __syncthreads();
-
-    // horizontally interpolated values of one staged source row, for this thread's columns
-    auto hrow = [&](int v, int rowoff, float (&H)[C][COLS]) {
-      const float* base = vsm + g.view_off[v] + rowoff;
-      const int plane = sr[v].plane;
-#pragma unroll
-      for (int col = 0; col < COLS; col++) {
-        const float4 ct = coltab[v * g.BW + xl0 + col];
-        const int oa = __float_as_int(ct.x), ob = __float_as_int(ct.y);
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          float va = base[c * plane + oa], vb = base[c * plane + ob];
-          H[c][col] = __fmaf_rn(ct.z, va, __fmul_rn(ct.w, vb));
-        }
-      }
+    const float* buf = vsm + b * g.buf_floats;
+    // base of view v inside the staging buffer, including the 0..3-float alignment shift of this tile's run
+    auto view_base = [&](int v) -> const float* {
+      const ViewDev& vw = p.view[v];
+      const unsigned int sh = (unsigned int)((reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) >> 2) & 3u);
+      return buf + g.view_off[v] + sh;
     };
 
-    unsigned long long cnt_lo = 0, cnt_hi = 0;
-    const bool col_ok = worker && (xl0 + COLS <= bw);
-    const int ys = strip * g.rows_per_strip;
-    const int ye = min(ys + g.rows_per_strip, bh);
-
-    if (col_ok && ys < ye && need_scores) {
-      // ---- C. stream down the strip ----------------------------------------------------------------------------
-      float Ha[V][C][COLS], Hb[V][C][COLS];
+    u64 cnt_lo = 0, cnt_hi = 0;
+    float madd[C];
 #pragma unroll
-      for (int v = 0; v < V; v++) {
-        const float4 e = rowtab[v * g.BH + ys];
-        hrow(v, __float_as_int(e.z), Ha[v]);
-        hrow(v, __float_as_int(e.w), Hb[v]);
-      }
-      const int x = x0 + xl0;
+    for (int c = 0; c < C; c++) madd[c] = ((tp.bits >> c) & 1u) ? 0.f : -INFINITY;
+    const bool fast_ok = p.dec.mask_mode != PISTO_MASK_MULTIPLY;
+
+    if (worker && ys < ye && need_scores) {
+      u64 Ha[V][C], Hb[V][C];
+      const long long pix0 = ((long long)n * T_h + ys) * T_w + x;
+      const uint8_t* bgp = p.bg ? p.bg + pix0 : nullptr;
+      const uint8_t* gtp = do_conf ? p.gt + pix0 : nullptr;
+      uint8_t* lbp = p.label_out ? p.label_out + pix0 : nullptr;
+      int low_wait = need_low ? ((ys + p.low_fh - 1 - p.low_fh / 2) / p.low_fh) * p.low_fh + p.low_fh / 2 - ys : 0x7fffffff;
 #pragma unroll 1
       for (int yl = ys; yl < ye; yl++) {
-        const int y = y0 + yl;
-        const long long pix = ((long long)n * p.T_h + y) * p.T_w + x;
-        // issue the byte loads early; they are consumed after the view loop
-        unsigned int bgv[COLS], gtv[COLS];
-#pragma unroll
-        for (int col = 0; col < COLS; col++) {
-          bgv[col] = p.bg ? (unsigned int)__ldg(p.bg + pix + col) : 0xffffffffu;
-          gtv[col] = do_conf ? (unsigned int)__ldg(p.gt + pix + col) : 0xffu;
-        }
-        float acc[C][COLS];
+        const unsigned int flags = rowflags[yl];
+        unsigned int bg2 = 0xffffu, gt2 = 0xffffu;
+        if (bgp) bg2 = __ldg(reinterpret_cast<const unsigned short*>(bgp));
+        if (gtp) gt2 = __ldg(reinterpret_cast<const unsigned short*>(gtp));
+        u64 acc[C];
 #pragma unroll
         for (int v = 0; v < V; v++) {
-          const float4 e = rowtab[v * g.BH + yl];
-          const int fx = __float_as_int(e.x), fy = __float_as_int(e.y);
-          if ((fx | fy) < 0) {  // the source-row pair moved
-            if (fy < 0) {
-              hrow(v, __float_as_int(e.z), Ha[v]);
-            } else {
+          const unsigned int f = (flags >> (2 * v)) & 3u;
+          if (f) {  // the bracketing source rows moved: shift (f == 1) or reload both (f == 2)
+            const int2 ro = rowoff[v * T_h + yl];
+            const float* vb = view_base(v);
+            const int plane = g.view_plane[v];
+            const float4 c0 = coltab[v * T_w + x], c1 = coltab[v * T_w + x + 1];
+            const u64 w0 = pack2(c0.z, c1.z), w1 = pack2(c0.w, c1.w);
+            const int oa0 = __float_as_int(c0.x), ob0 = __float_as_int(c0.y), oa1 = __float_as_int(c1.x), ob1 = __float_as_int(c1.y);
+#pragma unroll 1
+            for (int r = (f == 2u ? 0 : 1); r < 2; r++) {
+              const float* rb = vb + (r == 0 ? ro.x : ro.y);
 #pragma unroll
-              for (int c = 0; c < C; c++)
-#pragma unroll
-                for (int col = 0; col < COLS; col++) Ha[v][c][col] = Hb[v][c][col];
-            }
-            hrow(v, __float_as_int(e.w), Hb[v]);
-          }
-          const float l0 = fabsf(e.x), l1 = fabsf(e.y);
-          float u[C][COLS];
-#pragma unroll
-          for (int c = 0; c < C; c++)
-#pragma unroll
-            for (int col = 0; col < COLS; col++) u[c][col] = __fmaf_rn(l0, Ha[v][c][col], __fmul_rn(l1, Hb[v][c][col]));
-          if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) {
-#pragma unroll
-            for (int col = 0; col < COLS; col++) {
-              float t[C];
-#pragma unroll
-              for (int c = 0; c < C; c++) t[c] = u[c][col];
-              pisto_softmax_inplace<C>(t);
-#pragma unroll
-              for (int c = 0; c < C; c++) u[c][col] = t[c];
+              for (int c = 0; c < C; c++) {
+                Ha[v][c] = Hb[v][c];
+                const float* pc = rb + c * plane;
+                Hb[v][c] = fma2(w0, pack2(pc[oa0], pc[oa1]), mul2(w1, pack2(pc[ob0], pc[ob1])));
+              }
             }
           }
+          const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(&rowtab[v * T_h + yl]);
+          u64 u[C];
 #pragma unroll
-          for (int c = 0; c < C; c++)
+          for (int c = 0; c < C; c++) u[c] = fma2(w.x, Ha[v][c], mul2(w.y, Hb[v][c]));
+          if (PROB) {
+            float s0[C], s1[C];
 #pragma unroll
-            for (int col = 0; col < COLS; col++) acc[c][col] = (v == 0) ? u[c][col] : __fadd_rn(acc[c][col], u[c][col]);
+            for (int c = 0; c < C; c++) unpack2(u[c], s0[c], s1[c]);
+            pisto_softmax_inplace<C>(s0);
+            pisto_softmax_inplace<C>(s1);
+#pragma unroll
+            for (int c = 0; c < C; c++) u[c] = pack2(s0[c], s1[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) acc[c] = (v == 0) ? u[c] : add2(acc[c], u[c]);
         }
-        // ---- D. per-pixel epilogue ----------------------------------------------------------------------------
-        unsigned int labs[COLS];
+        // ---- per-pixel epilogue -----------------------------------------------------------------------------
+        float a0[C], a1[C];
 #pragma unroll
-        for (int col = 0; col < COLS; col++) {
+        for (int c = 0; c < C; c++) unpack2(acc[c], a0[c], a1[c]);
+        int lab0, lab1;
+        if (tp.single >= 0) { lab0 = lab1 = tp.single; }
+        else {
+          lab0 = decide_px<C>(a0, madd, tp.bits, p.dec, fast_ok);
+          lab1 = decide_px<C>(a1, madd, tp.bits, p.dec, fast_ok);
+        }
+        if (do_conf) {
+          const unsigned int g0 = gt2 & 0xffu, g1 = gt2 >> 8;
+          if (g0 < (unsigned)C) { const unsigned int bn = g0 * C + lab0; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
+          if (g1 < (unsigned)C) { const unsigned int bn = g1 * C + lab1; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
+        }
+        if (lbp) {
+          const unsigned int o0 = ((bg2 & 0xffu) == (unsigned)p.bg_match && bgp) ? (unsigned)p.bg_label : (unsigned)lab0;
+          const unsigned int o1 = ((bg2 >> 8) == (unsigned)p.bg_match && bgp) ? (unsigned)p.bg_label : (unsigned)lab1;
+          *reinterpret_cast<unsigned short*>(lbp) = (unsigned short)(o0 | (o1 << 8));
+          lbp += T_w;
+        }
+        if (bgp) bgp += T_w;
+        if (gtp) gtp += T_w;
+        if (p.fused_out) {
+          float* fo = p.fused_out + (((long long)n * C) * T_h + yl) * T_w + x;
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            *reinterpret_cast<float2*>(fo + (long long)c * T_h * T_w) = make_float2(pisto_div_views(a0[c], p.dec), pisto_div_views(a1[c], p.dec));
+        }
+        if (yl - ys == low_wait) {
+          low_wait += p.low_fh;
+          if (lowcol_mask) {
+            const int ly = yl / p.low_fh;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              float* lo = p.lowres_out + (((long long)n * C + c) * p.low_h + ly) * p.low_w;
+              if (lowcol_mask & 1) lo[x / p.low_fw] = pisto_div_views(a0[c], p.dec);
+              if (lowcol_mask & 2) lo[(x + 1) / p.low_fw] = pisto_div_views(a1[c], p.dec);
+            }
+          }
+        }
+      }
+    } else if (!need_scores) {
+      // single-label tile (infer_pseudo_masks.py:71-73): constant label + background overwrite, 16 pixels per thread-step
+      const long long tpx = (long long)T_h * T_w;
+      const long long base = (long long)n * tpx;
+      const unsigned int lab4 = 0x01010101u * (unsigned)tp.single, bgl4 = 0x01010101u * (unsigned)p.bg_label;
+      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
+      const long long nvec = vec_ok ? tpx / 16 : 0;
+      for (long long i = tid; i < nvec; i += nt) {
+        uint4 o = make_uint4(lab4, lab4, lab4, lab4);
+        if (p.bg) {
+          const uint4 bgv = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+          const unsigned int m = 0x01010101u * (unsigned)p.bg_match;
+          auto sel = [&](unsigned int w) -> unsigned int {
+            const unsigned int eq = __vcmpeq4(w, m);  // 0xff in every byte equal to bg_match
+            return (bgl4 & eq) | (lab4 & ~eq);
+          };
+          o = make_uint4(sel(bgv.x), sel(bgv.y), sel(bgv.z), sel(bgv.w));
+        }
+        if (do_conf) {
+          const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+          const unsigned int gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const unsigned int gg = (gw[q] >> (8 * j)) & 0xffu;
+              if (gg < (unsigned)C) { const unsigned int bn = gg * C + tp.single; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
+            }
+        }
+        if (p.label_out) reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
+      }
+      for (long long i = nvec * 16 + tid; i < tpx; i += nt) {  // unaligned / ragged remainder
+        unsigned int o = (unsigned)tp.single;
+        if (p.bg && p.bg[base + i] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+        if (do_conf) {
+          const unsigned int gg = p.gt[base + i];
+          if (gg < (unsigned)C) { const unsigned int bn = gg * C + tp.single; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
+        }
+        if (p.label_out) p.label_out[base + i] = (uint8_t)o;
+      }
+      if (need_low) {
+        // the 32x32 logits are exported before the shortcut (infer_pseudo_masks.py:126): evaluate the gather points only
+        const int npt = p.low_h * p.low_w;
+        for (int i = tid; i < npt; i += nt) {
+          const int ly = i / p.low_w, lx = i - ly * p.low_w;
+          const int yy = ly * p.low_fh + p.low_fh / 2, xx = lx * p.low_fw + p.low_fw / 2;
           float a[C];
 #pragma unroll
-          for (int c = 0; c < C; c++) a[c] = acc[c][col];
-          int lab = (tp.single >= 0) ? tp.single : pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
-          if (do_conf && gtv[col] < (unsigned)C) {
-            unsigned int b = gtv[col] * C + lab;
-            unsigned long long inc = 1ull << (8 * (b & 7));
-            if (b < 8) cnt_lo += inc; else cnt_hi += inc;
-          }
-          labs[col] = (bgv[col] == (unsigned int)p.bg_match) ? (unsigned int)p.bg_label : (unsigned int)lab;
-        }
-        if (p.label_out) {
-          if (COLS == 2) {
-            *reinterpret_cast<uchar2*>(p.label_out + pix) = make_uchar2((unsigned char)labs[0], (unsigned char)labs[COLS - 1]);
-          } else {
+          for (int v = 0; v < V; v++) {
+            const float4 er = rowtab[v * T_h + yy];
+            const int2 ro = rowoff[v * T_h + yy];
+            const float4 ec = coltab[v * T_w + xx];
+            const float* vb = view_base(v);
+            const int plane = g.view_plane[v];
+            const int oa = __float_as_int(ec.x), ob = __float_as_int(ec.y);
+            float u[C];
 #pragma unroll
-            for (int col = 0; col < COLS; col++) p.label_out[pix + col] = (unsigned char)labs[col];
-          }
-        }
-        if (p.fused_out) {
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            float* fo = p.fused_out + (((long long)n * C + c) * p.T_h + y) * p.T_w + x;
-            if (COLS == 2) {
-              *reinterpret_cast<float2*>(fo) = make_float2(pisto_div_views(acc[c][0], p.dec), pisto_div_views(acc[c][COLS - 1], p.dec));
-            } else {
-#pragma unroll
-              for (int col = 0; col < COLS; col++) fo[col] = pisto_div_views(acc[c][col], p.dec);
+            for (int c = 0; c < C; c++) {
+              const float* pl = vb + c * plane;
+              const float h0 = __fmaf_rn(ec.z, pl[ro.x + oa], __fmul_rn(ec.w, pl[ro.x + ob]));
+              const float h1 = __fmaf_rn(ec.z, pl[ro.y + oa], __fmul_rn(ec.w, pl[ro.y + ob]));
+              u[c] = __fmaf_rn(er.x, h0, __fmul_rn(er.z, h1));
             }
+            if (PROB) pisto_softmax_inplace<C>(u);
+#pragma unroll
+            for (int c = 0; c < C; c++) a[c] = (v == 0) ? u[c] : __fadd_rn(a[c], u[c]);
           }
+#pragma unroll
+          for (int c = 0; c < C; c++) p.lowres_out[((long long)n * C + c) * npt + i] = pisto_div_views(a[c], p.dec);
         }
-        if (need_low && (y % p.low_fh == p.low_fh / 2)) {
-#pragma unroll
-          for (int col = 0; col < COLS; col++) {
-            if ((x + col) % p.low_fw == p.low_fw / 2) {
-#pragma unroll
-              for (int c = 0; c < C; c++)
-                p.lowres_out[(((long long)n * C + c) * p.low_h + y / p.low_fh) * p.low_w + (x + col) / p.low_fw] =
-                    pisto_div_views(acc[c][col], p.dec);
-            }
-          }
-        }
-      }
-    } else if (col_ok && ys < ye) {
-      // single-label tile (infer_pseudo_masks.py:71-73): constant label, background overwrite, no scores read
-      const int x = x0 + xl0;
-      for (int yl = ys; yl < ye; yl++) {
-        const long long pix = ((long long)n * p.T_h + y0 + yl) * p.T_w + x;
-#pragma unroll
-        for (int col = 0; col < COLS; col++) {
-          unsigned int bgv = p.bg ? (unsigned int)__ldg(p.bg + pix + col) : 0xffffffffu;
-          if (do_conf) {
-            unsigned int gv = __ldg(p.gt + pix + col);
-            if (gv < (unsigned)C) {
-              unsigned int b = gv * C + tp.single;
-              unsigned long long inc = 1ull << (8 * (b & 7));
-              if (b < 8) cnt_lo += inc; else cnt_hi += inc;
-            }
-          }
-          if (p.label_out) p.label_out[pix + col] = (unsigned char)((bgv == (unsigned int)p.bg_match) ? p.bg_label : tp.single);
-        }
-      }
-    }
-    if (!need_scores && need_low) {
-      // single-label tile whose 32x32 logits are still exported (infer_pseudo_masks.py:126 precedes the shortcut):
-      // evaluate the fused scores only at the gather points of this block
-      const int ly0 = (y0 + p.low_fh - 1 - p.low_fh / 2) / p.low_fh;  // first low row with centre >= y0
-      const int lx0 = (x0 + p.low_fw - 1 - p.low_fw / 2) / p.low_fw;
-      const int ytop = y0 + bh - 1 - p.low_fh / 2, xtop = x0 + bw - 1 - p.low_fw / 2;
-      const int ly1 = ytop < 0 ? 0 : min(p.low_h, ytop / p.low_fh + 1);
-      const int lx1 = xtop < 0 ? 0 : min(p.low_w, xtop / p.low_fw + 1);
-      const int nly = max(ly1 - ly0, 0), nlx = max(lx1 - lx0, 0);
-      for (int i = tid; i < nly * nlx; i += nt) {
-        const int ly = ly0 + i / nlx, lx = lx0 + i % nlx;
-        const int yl = ly * p.low_fh + p.low_fh / 2 - y0, xl = lx * p.low_fw + p.low_fw / 2 - x0;
-        float a[C];
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const float4 er = rowtab[v * g.BH + yl];
-          const float4 ec = coltab[v * g.BW + xl];
-          const float* base = vsm + g.view_off[v];
-          const int plane = sr[v].plane;
-          const int r0 = __float_as_int(er.z), r1 = __float_as_int(er.w), oa = __float_as_int(ec.x), ob = __float_as_int(ec.y);
-          const float l0 = fabsf(er.x), l1 = fabsf(er.y);
-          float u[C];
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            const float* pl = base + c * plane;
-            float h0 = __fmaf_rn(ec.z, pl[r0 + oa], __fmul_rn(ec.w, pl[r0 + ob]));
-            float h1 = __fmaf_rn(ec.z, pl[r1 + oa], __fmul_rn(ec.w, pl[r1 + ob]));
-            u[c] = __fmaf_rn(l0, h0, __fmul_rn(l1, h1));
-          }
-          if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) pisto_softmax_inplace<C>(u);
-#pragma unroll
-          for (int c = 0; c < C; c++) a[c] = (v == 0) ? u[c] : __fadd_rn(a[c], u[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < C; c++)
-          p.lowres_out[(((long long)n * C + c) * p.low_h + ly) * p.low_w + lx] = pisto_div_views(a[c], p.dec);
       }
     }
     if (do_conf) {
       // every lane of every warp reaches this point: full-mask warp reductions are safe
 #pragma unroll
-      for (int b = 0; b < BINS; b++) {
-        unsigned int v = (unsigned int)(((b < 8 ? cnt_lo : cnt_hi) >> (8 * (b & 7))) & 0xffull);
-        v = __reduce_add_sync(0xffffffffu, v);
-        if ((tid & 31) == 0 && v) atomicAdd(&hist[b], v);
+      for (int bn = 0; bn < BINS; bn++) {
+        unsigned int cv = (unsigned int)(((bn < 8 ? cnt_lo : cnt_hi) >> (8 * (bn & 7))) & 0xffull);
+        cv = __reduce_add_sync(0xffffffffu, cv);
+        if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
       }
     }
+    __syncthreads();  // everyone is done with staging buffer b and has seen ctl->tile[b ^ 1]
   }
   if (do_conf) {
     __syncthreads();
     for (int i = tid; i < BINS; i += nt)
-      if (hist[i]) atomicAdd(&p.conf[i], (unsigned long long)hist[i]);
+      if (ctl->hist[i]) atomicAdd(&p.conf[i], (unsigned long long)ctl->hist[i]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// host side: geometry
+// host side
 // ---------------------------------------------------------------------------------------------------------------
-static int view_block_floats(const ViewDev& vw, int C, int y0, int bh, int x0, int bw) {
-  const ViewMap& m = vw.map;
-  int r_lo = pisto_src_index(vw.scale_h, y0, m.ho, vw.same_h).i0;
-  int r_hi = pisto_src_index(vw.scale_h, y0 + bh - 1, m.ho, vw.same_h).i1;
-  int c_lo = pisto_src_index(vw.scale_w, x0, m.wo, vw.same_w).i0;
-  int c_hi = pisto_src_index(vw.scale_w, x0 + bw - 1, m.wo, vw.same_w).i1;
-  int nr = r_hi - r_lo + 1, nc = c_hi - c_lo + 1;
-  // raw rows come from i when the map is not transposed (ai != 0), else from j
-  int nrows = m.ai != 0 ? nr : nc, pitch = m.ai != 0 ? nc : nr;
-  return C * nrows * pitch;
-}
-
-static bool make_geom(const pisto_ctx* h, const FuseParams& p, int COLS, StreamGeom* g) {
-  const int budget = h->smem_optin - 1024;
-  int BW = p.T_w;
-  const int max_bw = kMaxThreads * COLS;
-  if (BW > max_bw) {
-    int nb = (p.T_w + max_bw - 1) / max_bw;
-    BW = ((p.T_w + nb - 1) / nb + COLS - 1) / COLS * COLS;
-  }
-  if (BW % COLS) return false;
-  const int GX = BW / COLS;
+static bool make_geom(const pisto_ctx* h, const FuseParams& p, StreamGeom* g) {
+  if (p.T_w % 2) return false;
+  const int GX = p.T_w / 2;
+  if (GX > kMaxThreads) return false;
   int S = kMaxThreads / GX;
-  if (S < 1) return false;
-  // packed 8-bit confusion counters: rows_per_strip * COLS <= 255
-  for (int BH = p.T_h; BH >= 8; BH = (BH + 1) / 2) {
-    int s_eff = S;
-    if (s_eff > BH) s_eff = BH;
-    int rps = (BH + s_eff - 1) / s_eff;
-    if (rps * COLS > 255) continue;
-    StreamGeom t;
-    t.BW = BW; t.BH = BH;
-    t.nbx = (p.T_w + BW - 1) / BW; t.nby = (p.T_h + BH - 1) / BH;
-    t.GX = GX; t.S = s_eff; t.rows_per_strip = rps;
-    int off = 0;
-    t.sr_off = off; off += (int)sizeof(SubRect) * PISTO_MAX_VIEWS;
-    t.rowtab_off = off; off += 16 * p.V * BH;
-    t.coltab_off = off; off += 16 * p.V * BW;
-    t.hist_off = off; off += 4 * 64;
-    t.views_off = off;
-    int fl = 0;
-    for (int v = 0; v < p.V; v++) {
-      int cap = 0;
-      for (int by = 0; by < t.nby; by++)
-        for (int bx = 0; bx < t.nbx; bx++) {
-          int y0 = by * BH, x0 = bx * BW;
-          int bh = p.T_h - y0 < BH ? p.T_h - y0 : BH, bw = p.T_w - x0 < BW ? p.T_w - x0 : BW;
-          int f = view_block_floats(p.view[v], p.C, y0, bh, x0, bw);
-          if (f > cap) cap = f;
-        }
-      cap = (cap + 3) & ~3;
-      t.view_off[v] = fl; t.view_cap[v] = cap; fl += cap;
-    }
-    off += 4 * fl;
-    t.smem_bytes = off;
-    t.n_items = (long long)p.N * t.nbx * t.nby;
-    if (off <= budget) { *g = t; return true; }
+  if (S > p.T_h) S = p.T_h;
+  const int rps = (p.T_h + S - 1) / S;
+  if (rps * 2 > 255) return false;  // packed 8-bit confusion counters
+  g->GX = GX; g->S = S; g->rows_per_strip = rps;
+  g->threads = (GX * S + 31) / 32 * 32;
+  if (g->threads < 64) g->threads = 64;
+  int fl = 0;
+  for (int v = 0; v < p.V; v++) {
+    const ViewDev& vw = p.view[v];
+    g->view_off[v] = fl;
+    g->view_plane[v] = vw.h * vw.w;
+    fl += (p.C * vw.h * vw.w + 3 /* alignment shift */ + 3 /* tail */ + 3) & ~3;
   }
-  return false;
+  g->buf_floats = fl;
+  int off = 0;
+  g->ctl_off = off; off += (int)((sizeof(Ctl) + 127) & ~127u);
+  g->flags_off = off; off += (4 * p.T_h + 15) & ~15;
+  g->rowoff_off = off; off += 8 * p.V * p.T_h; off = (off + 15) & ~15;
+  g->rowtab_off = off; off += 16 * p.V * p.T_h;
+  g->coltab_off = off; off += 16 * p.V * p.T_w;
+  off = (off + 127) & ~127;
+  g->views_off = off; off += 2 * 4 * fl;
+  g->smem_bytes = off;
+  return off <= h->smem_optin - 1024;
 }
 
-template <int C, int V, int COLS>
+template <int C, int V, bool PROB>
 int launch_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   StreamGeom g;
-  if (!make_geom(h, p, COLS, &g)) return PISTO_OK;  // not launched: caller falls back
-  auto kern = fuse_stream_kernel<C, V, COLS>;
+  if (!make_geom(h, p, &g)) return PISTO_OK;  // not launched: caller falls back
+  auto kern = fuse_stream_kernel<C, V, PROB>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  int threads = (g.GX * g.S + 31) / 32 * 32;
-  if (threads < 64) threads = 64;
-  long long grid = g.n_items < h->sm_count ? g.n_items : h->sm_count;
-  // two CTAs per SM when they fit, so that one CTA's staging overlaps the other's arithmetic
-  if (2 * g.smem_bytes + 2048 <= h->smem_optin && 2 * threads <= 1024 && g.n_items >= 2LL * h->sm_count) grid = 2LL * h->sm_count;
-  kern<<<(int)grid, threads, g.smem_bytes, st>>>(p, g);
+  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
+  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  const int grid = p.N < h->sm_count ? p.N : h->sm_count;
+  kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   *launched = true;
@@ -447,22 +489,25 @@ int launch_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched
 
 int pisto_launch_fuse_stream(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   *launched = false;
-  if (p.entropy_out) return PISTO_OK;                    // dead output in the reference: generic kernel only
-  if (p.T_w % 2 != 0) return PISTO_OK;
-  if (p.conf && p.gt && p.C > 4) return PISTO_OK;        // packed counters hold C*C <= 16 bins
-  // 2-byte / 8-byte vector accesses need even addresses
+  if (p.entropy_out) return PISTO_OK;              // dead output in the reference: generic kernel only
+  if (p.conf && p.gt && p.C > 4) return PISTO_OK;  // packed counters hold C*C <= 16 bins
+  // 2-byte / 8-byte vector accesses need even addresses; TMA source spans need a 16-byte aligned allocation start
   if (((uintptr_t)p.label_out | (uintptr_t)p.bg | (uintptr_t)p.gt) & 1) return PISTO_OK;
   if ((uintptr_t)p.fused_out & 7) return PISTO_OK;
-#define PISTO_CASE(CC, VV, COLS) \
-  if (p.C == CC && p.V == VV) return launch_cv<CC, VV, COLS>(h, p, st, launched);
-  PISTO_CASE(3, 1, 2)
-  PISTO_CASE(3, 2, 2)
-  PISTO_CASE(3, 6, 2)
-  PISTO_CASE(3, 8, 2)
-  PISTO_CASE(4, 1, 2)
-  PISTO_CASE(4, 2, 2)
-  PISTO_CASE(4, 6, 2)
-  PISTO_CASE(4, 10, 1)
+  for (int v = 0; v < p.V; v++)
+    if ((uintptr_t)p.view[v].logits & 15) return PISTO_OK;
+  const bool prob = p.fuse_mode == PISTO_FUSE_PROB_MEAN;
+#define PISTO_CASE(CC, VV)                                                        \
+  if (p.C == CC && p.V == VV) {                                                   \
+    if (prob) return launch_cv<CC, VV, true>(h, p, st, launched);                 \
+    return launch_cv<CC, VV, false>(h, p, st, launched);                          \
+  }
+  PISTO_CASE(3, 1)
+  PISTO_CASE(3, 2)
+  PISTO_CASE(3, 6)
+  PISTO_CASE(4, 1)
+  PISTO_CASE(4, 2)
+  PISTO_CASE(4, 6)
 #undef PISTO_CASE
   return PISTO_OK;
 }
