@@ -135,6 +135,10 @@ int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_view_t* views
 /* device-clock duration (CUDA events, first H2D start -> last D2H end) of the last *_host call on this handle */
 double pisto_last_pipeline_ms(pisto_handle_t h);
 
+/* Self-test hook: counts the float32 inputs a (all 2^32 bit patterns) for which the library's a / V shortcut differs
+ * from IEEE division; adds the count to *mismatches_dev (device).  Expected: 0. */
+int pisto_selftest_div(pisto_handle_t h, int V, unsigned long long* mismatches_dev, pisto_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------------- */
 /* bilinear resize, align_corners=False: replaces interpolate_tensor / F.interpolate(mode='bilinear') */
 /*   infer_pseudo_masks.py:89-90, segmentation_test.py:88-89,197, prepare_seg_inputs.py:116,131,137   */

@@ -67,6 +67,7 @@ SYMBOLS = {
     "pisto_fuse_argmax_confusion": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _vp]),
     "pisto_fuse_argmax_confusion_host": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _i]),
     "pisto_last_pipeline_ms": (_d, [_vp]),
+    "pisto_selftest_div": (_i, [_vp, _i, _vp, _vp]),
     "pisto_upsample_bilinear": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "pisto_stitch_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "pisto_canvas_normalize": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),

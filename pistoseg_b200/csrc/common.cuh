@@ -121,12 +121,25 @@ struct DecideCfg {
   int V;            // number of fused views (the divisor)
   float inv_v;      // 1/V when V is a power of two (exact), else 0
   float margin_abs; // 2e-6 * V : see finalize fast path
+  float fV;         // (float)V
+  float rcp_v;      // RN(1/V)
 };
 
+// a / V, correctly rounded (== IEEE division).  Power-of-two V: one multiply.  Otherwise the classic
+// reciprocal + one fma-residual correction (Markstein): q = a*r, e = fma(-V, q, a), q' = fma(e, r, q) with
+// r = RN(1/V); it returns the correctly rounded quotient whenever nothing under/overflows, which the magnitude guard
+// ensures (outside it: __fdiv_rn).  pisto_selftest_div checks q' == __fdiv_rn over ALL 2^32 inputs for a given V
+// (tests/test_gpu_ops.py::test_division_by_view_count_exhaustive).
 __device__ __forceinline__ float pisto_div_views(float a, const DecideCfg& cfg) {
   if (cfg.V == 1) return a;
   if (cfg.inv_v != 0.f) return __fmul_rn(a, cfg.inv_v);  // power of two: same correctly-rounded quotient
-  return __fdiv_rn(a, (float)cfg.V);
+  const float fa = fabsf(a);
+  if (fa > 1e-30f && fa < 1e30f) {
+    const float q = __fmul_rn(a, cfg.rcp_v);
+    const float e = __fmaf_rn(-cfg.fV, q, a);
+    return __fmaf_rn(e, cfg.rcp_v, q);
+  }
+  return __fdiv_rn(a, cfg.fV);
 }
 
 // Exact reference semantics for one pixel.  s[] are the fused scores (already divided by V).

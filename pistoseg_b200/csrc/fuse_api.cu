@@ -26,6 +26,8 @@ int pisto_build_fuse_params(const pisto_view_t* views, int V, const pisto_fuse_a
   p.dec.V = V;
   p.dec.inv_v = is_pow2(V) ? 1.0f / (float)V : 0.f;
   p.dec.margin_abs = 2e-6f * (float)V;
+  p.dec.fV = (float)V;
+  p.dec.rcp_v = 1.0f / (float)V;
   p.bg_match = a->bg_match; p.bg_label = a->bg_label;
   p.present = a->present; p.bg = a->bg; p.gt = a->gt;
   p.label_out = a->label_out; p.fused_out = a->fused_out; p.entropy_out = a->entropy_out; p.lowres_out = a->lowres_out;
@@ -94,5 +96,30 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
     rc = pisto_upsample_launch(h, a->fused_out, a->lowres_out, (long long)p.N * p.C, p.T_h, p.T_w, a->low_h, a->low_w, 0, st);
     if (rc != PISTO_OK) return rc;
   }
+  return PISTO_OK;
+}
+
+// ---- self-test hook: exhaustive check of the division-by-view-count shortcut ---------------------------------------
+namespace {
+__global__ void selftest_div_kernel(int V, unsigned long long* mismatches) {
+  DecideCfg cfg;
+  cfg.V = V; cfg.inv_v = 0.f; cfg.fV = (float)V; cfg.rcp_v = 1.0f / (float)V; cfg.margin_abs = 0.f; cfg.mask_mode = 0; cfg.decide_mode = 0;
+  unsigned long long bad = 0;
+  const unsigned long long total = 1ull << 32;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float a = __uint_as_float((unsigned int)i);
+    const float q1 = pisto_div_views(a, cfg), q2 = __fdiv_rn(a, (float)V);
+    if (__float_as_uint(q1) != __float_as_uint(q2) && !(q1 != q1 && q2 != q2)) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int pisto_selftest_div(pisto_handle_t h, int V, unsigned long long* mismatches_dev, pisto_stream_t stream) {
+  PISTO_REQUIRE(h && mismatches_dev && V >= 1, "pisto_selftest_div: bad argument");
+  PISTO_CUDA(cudaSetDevice(h->device));
+  selftest_div_kernel<<<h->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(V, mismatches_dev);
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
   return PISTO_OK;
 }

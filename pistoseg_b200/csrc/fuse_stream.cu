@@ -69,12 +69,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 
 struct StreamGeom {
   int GX, S, rows_per_strip, threads;
-  int view_off[PISTO_MAX_VIEWS];  // float offset of each view inside one staging buffer (16-byte aligned)
-  int view_plane[PISTO_MAX_VIEWS];
-  int buf_floats;                 // floats per staging buffer
-  int ctl_off, flags_off, rowoff_off, rowtab_off, coltab_off, views_off;  // byte offsets into dynamic smem
+  int view_off[PISTO_MAX_VIEWS];    // float offset of each view inside one staging buffer (16-byte aligned)
+  int plane_bytes[PISTO_MAX_VIEWS]; // h*w*4
+  int buf_floats;                   // floats per staging buffer
+  int ctl_off, flags_off, rowoff_off, rowtab_off, cola_off, colb_off, views_off;  // byte offsets into dynamic smem
   int smem_bytes;
-  int* counter;                   // global tile counter (zeroed before the launch)
+  int* counter;                     // global tile counter (zeroed before the launch)
 };
 
 struct Ctl {
@@ -82,6 +82,13 @@ struct Ctl {
   int tile[2];
   unsigned int hist[64];
 };
+
+// ---- explicit shared-memory accesses through 32-bit addresses (keeps the address arithmetic in 32 bits) ------------
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int2 lds_i2(uint32_t a) { int2 v; asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ int4 lds_i4(uint32_t a) { int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ ulonglong2 lds_u64x2(uint32_t a) { ulonglong2 v; asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a)); return v; }
 
 // first index of the maximum, the maximum and the runner-up of v[0..C)
 template <int C>
@@ -96,24 +103,33 @@ __device__ __forceinline__ void top2(const float (&v)[C], int& bi, float& bv, fl
   }
 }
 
-// Label of one pixel from the undivided view sums a[] (see pisto_decide in common.cuh for the proof sketch of the
-// fast path); madd[c] is 0 for usable classes and -inf for classes masked out by the tile's presence vector.
+// Labels of the two pixels of a packed pair from the undivided view sums acc[] (see pisto_decide in common.cuh for
+// the argument behind the fast path); madd2[c] is (0,0) for usable classes and (-inf,-inf) for classes masked out by
+// the tile's presence vector.
 template <int C>
-__device__ __forceinline__ int decide_px(const float (&a)[C], const float (&madd)[C], uint32_t present_bits, const DecideCfg& cfg,
-                                         bool fast_ok) {
-  float v[C];
-  float chk = a[0];
+__device__ __forceinline__ void decide_pair(const u64 (&acc)[C], const u64 (&madd2)[C], uint32_t present_bits, const DecideCfg& cfg,
+                                            bool fast_ok, int& lab0, int& lab1) {
+  float v0[C], v1[C];
+  u64 chk = acc[0];
 #pragma unroll
   for (int c = 0; c < C; c++) {
-    v[c] = __fadd_rn(a[c], madd[c]);
-    if (c) chk = __fadd_rn(chk, a[c]);
+    unpack2(add2(acc[c], madd2[c]), v0[c], v1[c]);
+    if (c) chk = add2(chk, acc[c]);
   }
-  int bi; float bv, sv;
-  top2<C>(v, bi, bv, sv);
-  const float margin = __fmaf_rn(fabsf(bv), 2.4e-7f, cfg.margin_abs);
-  const bool ok = fast_ok && (__fsub_rn(bv, sv) > margin) && (fabsf(chk) < 1e30f) && (bv > -1e9f);
-  if (ok) return bi;
-  return pisto_decide<C>(a, present_bits, cfg, false, nullptr);
+  float chk0, chk1;
+  unpack2(chk, chk0, chk1);
+  float bv0, sv0, bv1, sv1;
+  top2<C>(v0, lab0, bv0, sv0);
+  top2<C>(v1, lab1, bv1, sv1);
+  const bool ok0 = fast_ok && (__fsub_rn(bv0, sv0) > __fmaf_rn(fabsf(bv0), 2.4e-7f, cfg.margin_abs)) && (fabsf(chk0) < 1e30f) && (bv0 > -1e9f);
+  const bool ok1 = fast_ok && (__fsub_rn(bv1, sv1) > __fmaf_rn(fabsf(bv1), 2.4e-7f, cfg.margin_abs)) && (fabsf(chk1) < 1e30f) && (bv1 > -1e9f);
+  if (!(ok0 && ok1)) {  // near tie / NaN / absurd magnitude / MULTIPLY mask: follow the reference operation by operation
+    float a0[C], a1[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) unpack2(acc[c], a0[c], a1[c]);
+    if (!ok0) lab0 = pisto_decide<C>(a0, present_bits, cfg, false, nullptr);
+    if (!ok1) lab1 = pisto_decide<C>(a1, present_bits, cfg, false, nullptr);
+  }
 }
 
 template <int C, int V, bool PROB>
@@ -122,9 +138,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem_raw + g.ctl_off);
   unsigned int* rowflags = reinterpret_cast<unsigned int*>(smem_raw + g.flags_off);  // [T_h]
-  int2* rowoff = reinterpret_cast<int2*>(smem_raw + g.rowoff_off);                   // [V][T_h]
-  float4* rowtab = reinterpret_cast<float4*>(smem_raw + g.rowtab_off);               // [V][T_h] {l0,l0,l1,l1}
-  float4* coltab = reinterpret_cast<float4*>(smem_raw + g.coltab_off);               // [V][T_w] {oa,ob,l0,l1}
+  int2* rowoff = reinterpret_cast<int2*>(smem_raw + g.rowoff_off);                   // [T_h][V] byte offsets of rows i0, i1
+  float4* rowtab = reinterpret_cast<float4*>(smem_raw + g.rowtab_off);               // [T_h][V] {l0,l0,l1,l1}
+  int4* colA = reinterpret_cast<int4*>(smem_raw + g.cola_off);                       // [V][GX] byte offsets {i0,i1 of col 0; i0,i1 of col 1}
+  float4* colB = reinterpret_cast<float4*>(smem_raw + g.colb_off);                   // [V][GX] {l0 col0, l0 col1, l1 col0, l1 col1}
   float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);                     // 2 staging buffers
 
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -141,12 +158,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
   }
   for (int i = tid; i < 64; i += nt) ctl->hist[i] = 0;
   for (int i = tid; i < V * T_h; i += nt) {
-    const int v = i / T_h, y = i - v * T_h;
+    const int y = i / V, v = i - y * V;
     const ViewDev& vw = p.view[v];
     const int si2 = vw.map.ai * vw.w + vw.map.bi, base2 = vw.map.a0 * vw.w + vw.map.b0;
     const Lerp L = pisto_src_index(vw.scale_h, y, vw.map.ho, vw.same_h);
     rowtab[i] = make_float4(L.l0, L.l0, L.l1, L.l1);
-    rowoff[i] = make_int2(base2 + L.i0 * si2, base2 + L.i1 * si2);
+    rowoff[i] = make_int2(4 * (base2 + L.i0 * si2), 4 * (base2 + L.i1 * si2));
   }
   for (int y = tid; y < T_h; y += nt) {
     unsigned int f = 0;
@@ -162,12 +179,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
     }
     rowflags[y] = f;
   }
-  for (int i = tid; i < V * T_w; i += nt) {
-    const int v = i / T_w, x = i - v * T_w;
+  for (int i = tid; i < V * g.GX; i += nt) {
+    const int v = i / g.GX, gx = i - v * g.GX;
     const ViewDev& vw = p.view[v];
-    const int sj2 = vw.map.aj * vw.w + vw.map.bj;
-    const Lerp L = pisto_src_index(vw.scale_w, x, vw.map.wo, vw.same_w);
-    coltab[i] = make_float4(__int_as_float(L.i0 * sj2), __int_as_float(L.i1 * sj2), L.l0, L.l1);
+    const int sj2 = 4 * (vw.map.aj * vw.w + vw.map.bj);
+    const Lerp L0 = pisto_src_index(vw.scale_w, 2 * gx, vw.map.wo, vw.same_w);
+    const Lerp L1 = pisto_src_index(vw.scale_w, 2 * gx + 1, vw.map.wo, vw.same_w);
+    colA[i] = make_int4(L0.i0 * sj2, L0.i1 * sj2, L1.i0 * sj2, L1.i1 * sj2);
+    colB[i] = make_float4(L0.l0, L1.l0, L0.l1, L1.l1);
   }
 
   // does tile n read its views at all?  (single-label tiles without any score export do not)
@@ -213,12 +232,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
   const int x = 2 * grp;
   const int ys = strip * g.rows_per_strip;
   const int ye = min(ys + g.rows_per_strip, T_h);
-  // which of my two columns (if any) is a 32x32 gather column
-  int lowcol_mask = 0;
+  // 32x32 export: which of my two columns (if any) is a gather column, and its low-resolution column index
+  int lowcol_mask = 0, lx0 = 0, lx1 = 0;
   if (need_low) {
-    if (x % p.low_fw == p.low_fw / 2) lowcol_mask |= 1;
-    if ((x + 1) % p.low_fw == p.low_fw / 2) lowcol_mask |= 2;
+    if (x % p.low_fw == p.low_fw / 2) { lowcol_mask |= 1; lx0 = x / p.low_fw; }
+    if ((x + 1) % p.low_fw == p.low_fw / 2) { lowcol_mask |= 2; lx1 = (x + 1) / p.low_fw; }
   }
+  const int low_first = need_low ? ((ys + p.low_fh - 1 - p.low_fh / 2) / p.low_fh) : 0;  // first low row at or below ys
+  const uint32_t rowtab_s = smem_u32(rowtab), rowoff_s = smem_u32(rowoff), rowflags_s = smem_u32(rowflags);
+  const uint32_t colA_t = smem_u32(colA) + 16u * grp, colB_t = smem_u32(colB) + 16u * grp;
+  const uint32_t col_stride = 16u * g.GX;
   unsigned int uses0 = 0, uses1 = 0;  // completed phases of the two barriers
 
   for (int k = 0;; k++) {
@@ -238,56 +261,66 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
       mbar_wait(&ctl->mbar[b], ph & 1u);
       if (b) uses1++; else uses0++;
     }
-    const float* buf = vsm + b * g.buf_floats;
-    // base of view v inside the staging buffer, including the 0..3-float alignment shift of this tile's run
-    auto view_base = [&](int v) -> const float* {
+    // shared-memory byte address of view v's data in this tile's staging buffer (incl. the 0..3-float alignment shift)
+    uint32_t vb[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
       const ViewDev& vw = p.view[v];
-      const unsigned int sh = (unsigned int)((reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) >> 2) & 3u);
-      return buf + g.view_off[v] + sh;
-    };
+      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+      vb[v] = smem_u32(vsm + b * g.buf_floats + g.view_off[v]) + sh;
+    }
 
     u64 cnt_lo = 0, cnt_hi = 0;
-    float madd[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) madd[c] = ((tp.bits >> c) & 1u) ? 0.f : -INFINITY;
-    const bool fast_ok = p.dec.mask_mode != PISTO_MASK_MULTIPLY;
 
     if (worker && ys < ye && need_scores) {
+      u64 madd2[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) { const float m = ((tp.bits >> c) & 1u) ? 0.f : -INFINITY; madd2[c] = pack2(m, m); }
+      const bool fast_ok = p.dec.mask_mode != PISTO_MASK_MULTIPLY;
       u64 Ha[V][C], Hb[V][C];
+      // horizontally interpolated values of one staged source row (byte address `row`) for my two columns
+      auto load_h = [&](int v, uint32_t row, u64 (&H)[C]) {
+        const int4 A = lds_i4(colA_t + v * col_stride);
+        const ulonglong2 B = lds_u64x2(colB_t + v * col_stride);
+        uint32_t a00 = row + A.x, a01 = row + A.y, a10 = row + A.z, a11 = row + A.w;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const float p00 = lds_f32(a00), p01 = lds_f32(a01), p10 = lds_f32(a10), p11 = lds_f32(a11);
+          H[c] = fma2(B.x, pack2(p00, p10), mul2(B.y, pack2(p01, p11)));
+          if (c + 1 < C) { a00 += g.plane_bytes[v]; a01 += g.plane_bytes[v]; a10 += g.plane_bytes[v]; a11 += g.plane_bytes[v]; }
+        }
+      };
       const long long pix0 = ((long long)n * T_h + ys) * T_w + x;
       const uint8_t* bgp = p.bg ? p.bg + pix0 : nullptr;
       const uint8_t* gtp = do_conf ? p.gt + pix0 : nullptr;
       uint8_t* lbp = p.label_out ? p.label_out + pix0 : nullptr;
-      int low_wait = need_low ? ((ys + p.low_fh - 1 - p.low_fh / 2) / p.low_fh) * p.low_fh + p.low_fh / 2 - ys : 0x7fffffff;
+      float* fop = p.fused_out ? p.fused_out + (((long long)n * C) * T_h + ys) * T_w + x : nullptr;
+      float* lowp = need_low ? p.lowres_out + ((long long)n * C * p.low_h + low_first) * p.low_w : nullptr;
+      int low_next = need_low ? low_first * p.low_fh + p.low_fh / 2 : 0x7fffffff;
+      uint32_t rt = rowtab_s + 16u * V * ys, ro_a = rowoff_s + 8u * V * ys, fl_a = rowflags_s + 4u * ys;
 #pragma unroll 1
       for (int yl = ys; yl < ye; yl++) {
-        const unsigned int flags = rowflags[yl];
+        const unsigned int flags = lds_u32(fl_a);
         unsigned int bg2 = 0xffffu, gt2 = 0xffffu;
         if (bgp) bg2 = __ldg(reinterpret_cast<const unsigned short*>(bgp));
         if (gtp) gt2 = __ldg(reinterpret_cast<const unsigned short*>(gtp));
+        if (flags) {  // the bracketing source rows of at least one view moved
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const unsigned int f = (flags >> (2 * v)) & 3u;
+            if (f) {
+              const int2 ro = lds_i2(ro_a + 8u * v);
+              if (f == 2u) load_h(v, vb[v] + ro.x, Hb[v]);  // reload both (strip start / down-sampling views)
+#pragma unroll
+              for (int c = 0; c < C; c++) Ha[v][c] = Hb[v][c];
+              load_h(v, vb[v] + ro.y, Hb[v]);
+            }
+          }
+        }
         u64 acc[C];
 #pragma unroll
         for (int v = 0; v < V; v++) {
-          const unsigned int f = (flags >> (2 * v)) & 3u;
-          if (f) {  // the bracketing source rows moved: shift (f == 1) or reload both (f == 2)
-            const int2 ro = rowoff[v * T_h + yl];
-            const float* vb = view_base(v);
-            const int plane = g.view_plane[v];
-            const float4 c0 = coltab[v * T_w + x], c1 = coltab[v * T_w + x + 1];
-            const u64 w0 = pack2(c0.z, c1.z), w1 = pack2(c0.w, c1.w);
-            const int oa0 = __float_as_int(c0.x), ob0 = __float_as_int(c0.y), oa1 = __float_as_int(c1.x), ob1 = __float_as_int(c1.y);
-#pragma unroll 1
-            for (int r = (f == 2u ? 0 : 1); r < 2; r++) {
-              const float* rb = vb + (r == 0 ? ro.x : ro.y);
-#pragma unroll
-              for (int c = 0; c < C; c++) {
-                Ha[v][c] = Hb[v][c];
-                const float* pc = rb + c * plane;
-                Hb[v][c] = fma2(w0, pack2(pc[oa0], pc[oa1]), mul2(w1, pack2(pc[ob0], pc[ob1])));
-              }
-            }
-          }
-          const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(&rowtab[v * T_h + yl]);
+          const ulonglong2 w = lds_u64x2(rt + 16u * v);
           u64 u[C];
 #pragma unroll
           for (int c = 0; c < C; c++) u[c] = fma2(w.x, Ha[v][c], mul2(w.y, Hb[v][c]));
@@ -303,46 +336,49 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
 #pragma unroll
           for (int c = 0; c < C; c++) acc[c] = (v == 0) ? u[c] : add2(acc[c], u[c]);
         }
+        rt += 16u * V; ro_a += 8u * V; fl_a += 4u;
         // ---- per-pixel epilogue -----------------------------------------------------------------------------
-        float a0[C], a1[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) unpack2(acc[c], a0[c], a1[c]);
         int lab0, lab1;
         if (tp.single >= 0) { lab0 = lab1 = tp.single; }
-        else {
-          lab0 = decide_px<C>(a0, madd, tp.bits, p.dec, fast_ok);
-          lab1 = decide_px<C>(a1, madd, tp.bits, p.dec, fast_ok);
-        }
+        else decide_pair<C>(acc, madd2, tp.bits, p.dec, fast_ok, lab0, lab1);
         if (do_conf) {
           const unsigned int g0 = gt2 & 0xffu, g1 = gt2 >> 8;
           if (g0 < (unsigned)C) { const unsigned int bn = g0 * C + lab0; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
           if (g1 < (unsigned)C) { const unsigned int bn = g1 * C + lab1; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
+          gtp += T_w;
         }
         if (lbp) {
-          const unsigned int o0 = ((bg2 & 0xffu) == (unsigned)p.bg_match && bgp) ? (unsigned)p.bg_label : (unsigned)lab0;
-          const unsigned int o1 = ((bg2 >> 8) == (unsigned)p.bg_match && bgp) ? (unsigned)p.bg_label : (unsigned)lab1;
+          unsigned int o0 = (unsigned)lab0, o1 = (unsigned)lab1;
+          if (bgp) {
+            o0 = ((bg2 & 0xffu) == (unsigned)p.bg_match) ? (unsigned)p.bg_label : o0;
+            o1 = ((bg2 >> 8) == (unsigned)p.bg_match) ? (unsigned)p.bg_label : o1;
+            bgp += T_w;
+          }
           *reinterpret_cast<unsigned short*>(lbp) = (unsigned short)(o0 | (o1 << 8));
           lbp += T_w;
         }
-        if (bgp) bgp += T_w;
-        if (gtp) gtp += T_w;
-        if (p.fused_out) {
-          float* fo = p.fused_out + (((long long)n * C) * T_h + yl) * T_w + x;
+        if (fop) {
 #pragma unroll
-          for (int c = 0; c < C; c++)
-            *reinterpret_cast<float2*>(fo + (long long)c * T_h * T_w) = make_float2(pisto_div_views(a0[c], p.dec), pisto_div_views(a1[c], p.dec));
+          for (int c = 0; c < C; c++) {
+            float a0, a1;
+            unpack2(acc[c], a0, a1);
+            *reinterpret_cast<float2*>(fop + (long long)c * T_h * T_w) = make_float2(pisto_div_views(a0, p.dec), pisto_div_views(a1, p.dec));
+          }
+          fop += T_w;
         }
-        if (yl - ys == low_wait) {
-          low_wait += p.low_fh;
+        if (yl == low_next) {
+          low_next += p.low_fh;
           if (lowcol_mask) {
-            const int ly = yl / p.low_fh;
 #pragma unroll
             for (int c = 0; c < C; c++) {
-              float* lo = p.lowres_out + (((long long)n * C + c) * p.low_h + ly) * p.low_w;
-              if (lowcol_mask & 1) lo[x / p.low_fw] = pisto_div_views(a0[c], p.dec);
-              if (lowcol_mask & 2) lo[(x + 1) / p.low_fw] = pisto_div_views(a1[c], p.dec);
+              float a0, a1;
+              unpack2(acc[c], a0, a1);
+              float* lo = lowp + c * (p.low_h * p.low_w);
+              if (lowcol_mask & 1) lo[lx0] = pisto_div_views(a0, p.dec);
+              if (lowcol_mask & 2) lo[lx1] = pisto_div_views(a1, p.dec);
             }
           }
+          lowp += p.low_w;
         }
       }
     } else if (!need_scores) {
@@ -394,18 +430,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
           float a[C];
 #pragma unroll
           for (int v = 0; v < V; v++) {
-            const float4 er = rowtab[v * T_h + yy];
-            const int2 ro = rowoff[v * T_h + yy];
-            const float4 ec = coltab[v * T_w + xx];
-            const float* vb = view_base(v);
-            const int plane = g.view_plane[v];
-            const int oa = __float_as_int(ec.x), ob = __float_as_int(ec.y);
+            const float4 er = rowtab[yy * V + v];
+            const int2 ro = rowoff[yy * V + v];
+            const int4 A = colA[v * g.GX + (xx >> 1)];
+            const float4 B = colB[v * g.GX + (xx >> 1)];
+            const int oa = (xx & 1) ? A.z : A.x, ob = (xx & 1) ? A.w : A.y;
+            const float wl0 = (xx & 1) ? B.y : B.x, wl1 = (xx & 1) ? B.w : B.z;
             float u[C];
 #pragma unroll
             for (int c = 0; c < C; c++) {
-              const float* pl = vb + c * plane;
-              const float h0 = __fmaf_rn(ec.z, pl[ro.x + oa], __fmul_rn(ec.w, pl[ro.x + ob]));
-              const float h1 = __fmaf_rn(ec.z, pl[ro.y + oa], __fmul_rn(ec.w, pl[ro.y + ob]));
+              const uint32_t pl = vb[v] + c * g.plane_bytes[v];
+              const float h0 = __fmaf_rn(wl0, lds_f32(pl + ro.x + oa), __fmul_rn(wl1, lds_f32(pl + ro.x + ob)));
+              const float h1 = __fmaf_rn(wl0, lds_f32(pl + ro.y + oa), __fmul_rn(wl1, lds_f32(pl + ro.y + ob)));
               u[c] = __fmaf_rn(er.x, h0, __fmul_rn(er.z, h1));
             }
             if (PROB) pisto_softmax_inplace<C>(u);
@@ -453,7 +489,7 @@ static bool make_geom(const pisto_ctx* h, const FuseParams& p, StreamGeom* g) {
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
     g->view_off[v] = fl;
-    g->view_plane[v] = vw.h * vw.w;
+    g->plane_bytes[v] = 4 * vw.h * vw.w;
     fl += (p.C * vw.h * vw.w + 3 /* alignment shift */ + 3 /* tail */ + 3) & ~3;
   }
   g->buf_floats = fl;
@@ -462,7 +498,8 @@ static bool make_geom(const pisto_ctx* h, const FuseParams& p, StreamGeom* g) {
   g->flags_off = off; off += (4 * p.T_h + 15) & ~15;
   g->rowoff_off = off; off += 8 * p.V * p.T_h; off = (off + 15) & ~15;
   g->rowtab_off = off; off += 16 * p.V * p.T_h;
-  g->coltab_off = off; off += 16 * p.V * p.T_w;
+  g->cola_off = off; off += 16 * p.V * GX;
+  g->colb_off = off; off += 16 * p.V * GX;
   off = (off + 127) & ~127;
   g->views_off = off; off += 2 * 4 * fl;
   g->smem_bytes = off;

@@ -137,3 +137,14 @@ def test_argmax_f64_present_mask(cuda):
     assert np.array_equal(out["pred"].cpu().numpy(), ref.astype(np.uint8))
     out = ops.argmax_f64(e.to(cuda), want_labels=False)
     assert np.array_equal(out["pred"].cpu().numpy(), e.numpy().argmax(0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("V", [3, 5, 6, 7, 10, 12])
+def test_division_by_view_count_exhaustive(cuda, V):
+    """The 3-instruction a / V used for the fused-score exports equals IEEE division for ALL 2^32 float inputs."""
+    import ctypes
+    from pistoseg_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    _lib.check(_lib.load().pisto_selftest_div(_lib.handle(0), V, ctypes.c_void_p(bad.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert int(bad.cpu()) == 0
