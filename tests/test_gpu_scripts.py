@@ -1,0 +1,174 @@
+"""Script-level integration: the drop-in infer_pseudo_masks.py / segmentation_test.py driven with a stub backbone and a tiny
+synthetic dataset, their file outputs and reports compared with the reference procedure restated in oracle/."""
+import logging
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import confusion as oconf
+from oracle import fuse as ofuse
+from oracle import stitch as ostitch
+from oracle import tta as otta
+
+pytestmark = pytest.mark.gpu
+
+
+class StubBackbone(torch.nn.Module):
+    """Per-pixel affine map of the image + a fixed position-dependent bias: NOT equivariant under flips / rotations
+    (so the d4 merge matters) and built from single-rounding elementwise ops (bit-identical on CPU and GPU)."""
+
+    def __init__(self, C, size, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.register_buffer("a", torch.randn(C, generator=g))
+        self.register_buffer("bias", torch.randn((C, size, size), generator=g) * 2)
+        self.C = C
+
+    def forward(self, x):
+        ch = torch.stack([x[:, c % 3] for c in range(self.C)], 1)
+        return ch * self.a.view(1, -1, 1, 1) + self.bias.unsqueeze(0)
+
+
+class PseudoDataset(torch.utils.data.Dataset):
+    def __init__(self, n, size, labels, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.images = torch.randn((n, 3, size, size), generator=g)
+        self.tissue = torch.where(torch.rand((n, size, size), generator=g) < 0.2, 0.0, 127.0).double()
+        self.names = [f"{1000 + i}-{i}-{i}-{labels[i % len(labels)]}.png" for i in range(n)]
+
+    def __len__(self):
+        return len(self.names)
+
+    def __getitem__(self, i):
+        return {"image": self.images[i], "tissue": self.tissue[i], "name": self.names[i]}
+
+
+def test_infer_pseudo_masks_outputs(cuda, tmp_path):
+    import infer_pseudo_masks as script
+    size, n, C = 64, 10, 3
+    labels = ["[1, 1, 0]", "[0, 1, 0]", "[1, 1, 1]", "[1, 0, 1]"]
+    ds = PseudoDataset(n, size, labels, seed=3)
+    model = StubBackbone(C, size, seed=4)
+    orig = {name: (50 + 3 * i, 40 + 2 * i) for i, name in enumerate(ds.names)}   # (w, h) of the "original" tiles
+    args = types.SimpleNamespace(checkpoint=None, train_data=str(tmp_path), save_dir=str(tmp_path / "pmask"), gpus=0, dataset="wsss4luad",
+                                 batch_size=4, num_workers=0, pin_memory=False, patch_size=size)
+    script.main(args, model=model.to(cuda), dataset=ds, original_size=lambda name: orig[name])
+    for d in ("mask", "logits_32x32", "background-img", "entropy"):
+        assert (tmp_path / "pmask" / d).is_dir()
+    # reference procedure on the CPU (infer_pseudo_masks.py:118-154)
+    merged = otta.d4_merge_mean(model.cpu(), ds.images)
+    agree, total = 0, 0
+    for i, name in enumerate(ds.names):
+        low = torch.load(tmp_path / "pmask" / "logits_32x32" / (name.split(".png")[0] + ".pt"), map_location="cpu")
+        ref_low = ofuse.lowres_32(merged[i:i + 1], literal=True)[0]
+        assert low.shape == (C, 32, 32) and low.dtype == torch.float32
+        assert float(((low - ref_low).abs() / ref_low.abs().clamp_min(1)).max()) <= 1e-5
+        lab = script.label_from_name(name, "wsss4luad")
+        mask, _ = ofuse.get_mask_pred_and_entropy(merged[i].clone(), ds.tissue[i].numpy(), lab)
+        ref_png = Image.fromarray(np.uint8(mask), mode="P").resize(orig[name], resample=Image.BILINEAR)
+        got = Image.open(tmp_path / "pmask" / "mask" / name)
+        assert got.mode == "P" and got.size == orig[name]
+        assert got.getpalette()[:12] == [0, 64, 128, 64, 128, 0, 243, 152, 0, 255, 255, 255]
+        a, b = np.array(got), np.array(ref_png)
+        agree += (a == b).sum(); total += a.size
+    assert agree / total >= 0.9999
+
+
+class PatchDataset(torch.utils.data.Dataset):
+    """Tiles of two images cut at 3 scales with stride P/2, reflect-free (tiles are fully inside), named like
+    split_validation.ipynb does."""
+
+    def __init__(self, P, C, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.sizes = {"00": (90, 120), "01": (75, 70)}   # (h, w)
+        self.items = []
+        for idx, (h, w) in self.sizes.items():
+            for scale in (1.0, 1.25, 1.5):
+                hs, ws = int(h * scale), int(w * scale)
+                ys = sorted(set(list(range(0, max(hs - P, 0) + 1, P // 2)) + [max(hs - P, 0)]))
+                xs = sorted(set(list(range(0, max(ws - P, 0) + 1, P // 2)) + [max(ws - P, 0)]))
+                for y in ys:
+                    for x in xs:
+                        oh, ow = min(P, hs - y), min(P, ws - x)
+                        img = torch.randn((3, P, P), generator=g)
+                        msk = torch.randint(0, 4, (P, P), generator=g)
+                        self.items.append((img, msk, f"{idx}_{scale}_{y}_{x}-[1, 1, 1].png", oh, ow))
+        self.gt = {idx: torch.randint(0, 4, hw, generator=g).numpy().astype(np.uint8) for idx, hw in self.sizes.items()}
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+
+def test_segmentation_test_report(cuda, tmp_path, capsys):
+    import segmentation_test as script
+    P, C = 48, 3
+    ds = PatchDataset(P, C, seed=11)
+    model = StubBackbone(C, P, seed=12)
+    args = types.SimpleNamespace(dataset="wsss4luad", checkpoint=str(tmp_path), patch_size=P, test_data=str(tmp_path / "patches"), batch_size=7,
+                                 gpus=[0], num_workers=0, pin_memory=False, save_dir=str(tmp_path / "test"))
+    test_iou, big_iou = script.main(args, model=model.to(cuda), dataset=ds, image_size=lambda i: (ds.sizes[i][1], ds.sizes[i][0]),
+                                    load_gt=lambda i: ds.gt[i])
+    out = capsys.readouterr().out
+    assert "mIoU(big mask):" in out and "tIoU, sIoU, nIoU:" in out and "0/" in out
+    # reference procedure on the CPU
+    model = model.cpu()
+    cm_patch = np.zeros((3, 3))
+    tiles = {idx: [] for idx in ds.sizes}
+    for img, msk, name, oh, ow in ds.items:
+        logit = model(img[None])[0]
+        cm_patch += oconf.generate_matrix(ofuse.miou_pred(logit[None]).numpy()[0], msk.numpy(), 3)
+        idx, scale, pos = script.parse_tile_name(name)
+        tiles[idx].append((logit, scale, pos, (oh, ow)))
+    assert np.abs(test_iou.confusion_matrix - cm_patch).sum() <= 2e-4 * cm_patch.sum()
+    cm_big = np.zeros((3, 3))
+    for idx, (h, w) in ds.sizes.items():
+        probs = ostitch.big_mask_fuse(tiles[idx], (h, w))
+        pred, lab = ostitch.big_mask_labels(probs, ds.gt[idx])
+        cm_big += oconf.generate_matrix(pred, ds.gt[idx], 3)
+        got = np.array(Image.open(tmp_path / "test" / "mask" / f"{idx}.png"))
+        assert got.shape == (h, w) and (got == lab).mean() >= 0.9999
+    assert np.abs(big_iou.confusion_matrix - cm_big).sum() <= 2e-4 * cm_big.sum()
+    assert abs(big_iou.Mean_Intersection_over_Union() - oconf.mean_iou(cm_big)) < 1e-3
+
+
+def test_miou_mask_dropin_matches_reference_fixture(cuda):
+    """pistoseg_b200.metrics.mIoUMask against the fixture produced by the reference's own loss.py."""
+    from loss import mIoUMask
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "miou.npz"))
+    for tag, C in (("luad", 3), ("bcss", 4), ("empty", 3)):
+        m = mIoUMask(num_classes=C)
+        r1 = m(torch.from_numpy(z[f"{tag}_logits1"]).to(cuda), torch.from_numpy(z[f"{tag}_mask1"].astype(np.int64)).to(cuda))
+        assert np.allclose(np.array(r1), z[f"{tag}_ret1"], rtol=0, atol=1e-12)
+        m(torch.softmax(torch.from_numpy(z[f"{tag}_logits2"]), 1).to(cuda), torch.from_numpy(z[f"{tag}_mask2"].astype(np.int64)).to(cuda), probs=True)
+        assert np.array_equal(m.confusion_matrix, z[f"{tag}_cm"])
+        assert np.array_equal(m.Tissue_Intersection_over_Union(), z[f"{tag}_tissue"])
+        assert m.Mean_Intersection_over_Union() == float(z[f"{tag}_miou"])
+        assert m.Frequency_Weighted_Intersection_over_Union() == float(z[f"{tag}_fwiou"])
+        # numpy entry points of the reference API
+        m.reset()
+        pred = ofuse.miou_pred(torch.from_numpy(z[f"{tag}_logits1"])).numpy()
+        m.add_batch(pred, z[f"{tag}_mask1"])
+        assert np.array_equal(m.confusion_matrix, oconf.generate_matrix(pred, z[f"{tag}_mask1"], C).astype(np.float64))
+
+
+def test_function_level_dropins(cuda):
+    from pistoseg_b200 import postproc
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pmask.npz"))
+    i = 0
+    while f"logit{i}" in z:
+        logit = torch.from_numpy(z[f"logit{i}"].copy()).to(cuda)
+        lab = [int(v) for v in z[f"label{i}"]]
+        low = postproc.interpolate_tensor(logit, (8, 8))
+        assert np.array_equal(low.cpu().numpy(), z[f"low{i}"])
+        mask, ent = postproc.get_mask_pred_and_entropy(logit, z[f"tissue{i}"], lab)
+        assert mask.dtype == np.int64 and (mask == z[f"mask{i}"]).mean() >= 0.9999
+        assert np.abs(np.asarray(ent, np.float32) - z[f"entropy{i}"]).max() <= 2e-5
+        assert np.array_equal(logit.cpu().numpy(), z[f"mutated{i}"]), "the reference's in-place -1e10 fill must be reproduced"
+        i += 1
