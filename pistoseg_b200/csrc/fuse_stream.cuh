@@ -63,13 +63,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMA prefetch of a contiguous global span into L2 (no shared-memory destination)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 struct StreamGeom {
-  int GX, S, rows_per_strip, threads;
+  int GX, S, rows_per_strip, threads;  // threads = compute warps * 32 + one producer warp
+  int cwarps;                          // compute warps
+  int strip_y0[17];                    // row range of strip s is [strip_y0[s], strip_y0[s+1])
   int view_off[PISTO_MAX_VIEWS];    // float offset of each view inside one staging buffer (16-byte aligned)
   int plane_bytes[PISTO_MAX_VIEWS]; // h*w*4
   int buf_floats;                   // floats per staging buffer
@@ -79,7 +88,8 @@ struct StreamGeom {
 };
 
 struct Ctl {
-  uint64_t mbar[2];
+  uint64_t full[2];   // producer -> consumers: tile id published (+ TMA bytes landed)
+  uint64_t empty[2];  // consumers -> producer: staging buffer may be refilled (one arrival per compute warp)
   int tile[2];
   unsigned int hist[64];
 };
@@ -159,8 +169,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
 
   // ---- one-time setup: barriers, tables ---------------------------------------------------------------------
   if (tid == 0) {
-    mbar_init(&ctl->mbar[0], 1);
-    mbar_init(&ctl->mbar[1], 1);
+    mbar_init(&ctl->full[0], 1);
+    mbar_init(&ctl->full[1], 1);
+    mbar_init(&ctl->empty[0], g.cwarps);
+    mbar_init(&ctl->empty[1], g.cwarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 64; i += nt) ctl->hist[i] = 0;
@@ -177,7 +189,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
     for (int v = 0; v < V; v++) {
       const ViewDev& vw = p.view[v];
       unsigned int fl = 2;  // first row of a strip: load both source rows
-      if (y % g.rows_per_strip != 0) {
+      bool strip_start = false;
+      for (int q = 0; q < g.S; q++) strip_start |= (y == g.strip_y0[q]);
+      if (!strip_start) {
         const Lerp L = pisto_src_index(vw.scale_h, y, vw.map.ho, vw.same_h);
         const Lerp P = pisto_src_index(vw.scale_h, y - 1, vw.map.ho, vw.same_h);
         fl = (P.i0 == L.i0 && P.i1 == L.i1) ? 0u : ((L.i0 == P.i1 && P.i1 == P.i0 + 1) ? 1u : 2u);
@@ -221,24 +235,42 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
         for (; t < end; t += 4) *reinterpret_cast<float*>(dst + (t - a0)) = *reinterpret_cast<const float*>(t);
       }
       const uint32_t bytes = (uint32_t)(a1 - a0);
-      if (bytes) bulk_g2s(dst, a0, bytes, &ctl->mbar[b]);
+      if (bytes) bulk_g2s(dst, a0, bytes, &ctl->full[b]);
       total += bytes;
     }
-    mbar_arrive_expect_tx(&ctl->mbar[b], total);
+    mbar_arrive_expect_tx(&ctl->full[b], total);
   };
 
-  if (tid == 0) {
-    const int t0 = atomicAdd(g.counter, 1);
-    ctl->tile[0] = t0 < p.N ? t0 : -1;
-    if (t0 < p.N && tile_needs_views(t0)) issue_tile(t0, 0);
-  }
-  __syncthreads();
+  __syncthreads();  // barriers + tables visible to every warp
 
+  const int ncomp = g.cwarps * 32;  // compute threads; the last warp of the CTA is the producer
+  if (tid >= ncomp) {
+    // ===== producer warp: claims tiles, publishes their ids, fetches their views (TMA) one tile ahead of the compute warps
+    if (tid == ncomp) {
+      const long long tile_px = (long long)T_h * T_w;
+      for (int k = 0;; k++) {
+        const int b = k & 1;
+        if (k >= 2) mbar_wait(&ctl->empty[b], ((k >> 1) - 1) & 1);  // all compute warps are done with buffer b
+        const int t = atomicAdd(g.counter, 1);
+        const int tile = t < p.N ? t : -1;
+        ctl->tile[b] = tile;
+        if (tile >= 0 && tile_needs_views(tile)) issue_tile(tile, b);
+        else mbar_arrive(&ctl->full[b]);
+        if (tile < 0) break;
+        // pull the tile's byte masks into L2 ahead of the per-row loads
+        if (tile_px % 16 == 0) {
+          if (has_bg && ((uintptr_t)p.bg & 15) == 0) bulk_prefetch_l2(p.bg + tile * tile_px, (uint32_t)tile_px);
+          if (do_conf && ((uintptr_t)p.gt & 15) == 0) bulk_prefetch_l2(p.gt + tile * tile_px, (uint32_t)tile_px);
+        }
+      }
+    }
+  } else {
+  // ===== compute warps
+  const int grp = tid % g.GX, strip = min(tid / g.GX, g.S - 1);
   const bool worker = tid < g.GX * g.S;
-  const int grp = tid % g.GX, strip = tid / g.GX;
   const int x = 2 * grp;
-  const int ys = strip * g.rows_per_strip;
-  const int ye = min(ys + g.rows_per_strip, T_h);
+  const int ys = g.strip_y0[strip];
+  const int ye = g.strip_y0[strip + 1];
   // 32x32 export: which of my two columns (if any) is a gather column, and its low-resolution column index
   int lowcol_mask = 0, lx0 = 0, lx1 = 0;
   if (need_low) {
@@ -249,25 +281,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
   const uint32_t rowtab_s = smem_u32(rowtab), rowoff_s = smem_u32(rowoff), rowflags_s = smem_u32(rowflags);
   const uint32_t colA_t = smem_u32(colA) + 16u * grp, colB_t = smem_u32(colB) + 16u * grp;
   const uint32_t col_stride = 16u * g.GX;
-  unsigned int uses0 = 0, uses1 = 0;  // completed phases of the two barriers
+  const int nt = ncomp;  // cooperative loops below run over the compute threads only
 
   for (int k = 0;; k++) {
     const int b = k & 1;
+    mbar_wait(&ctl->full[b], (k >> 1) & 1);  // tile id published, views (if any) landed
     const int n = ctl->tile[b];
     if (n < 0) break;
-    if (tid == 0) {
-      const int t1 = atomicAdd(g.counter, 1);
-      ctl->tile[b ^ 1] = t1 < p.N ? t1 : -1;
-      if (t1 < p.N && tile_needs_views(t1)) issue_tile(t1, b ^ 1);
-    }
     const TilePresence tp = pisto_tile_presence(p, n);
     const bool need_scores = tp.single < 0 || has_fused;
-    const bool staged = need_scores || need_low;
-    if (staged) {
-      const unsigned int ph = b ? uses1 : uses0;
-      mbar_wait(&ctl->mbar[b], ph & 1u);
-      if (b) uses1++; else uses0++;
-    }
     // shared-memory byte address of view v's data in this tile's staging buffer (incl. the 0..3-float alignment shift)
     uint32_t vb[V];
 #pragma unroll
@@ -496,8 +518,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
         if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
       }
     }
-    __syncthreads();  // everyone is done with staging buffer b and has seen ctl->tile[b ^ 1]
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&ctl->empty[b]);  // this warp is done with staging buffer b
   }
+  }  // compute warps
   if (do_conf) {
     __syncthreads();
     for (int i = tid; i < BINS; i += nt)
@@ -511,14 +535,60 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
 static bool make_geom(const pisto_ctx* h, const FuseParams& p, StreamGeom* g) {
   if (p.T_w % 2) return false;
   const int GX = p.T_w / 2;
-  if (GX > kMaxThreads) return false;
-  int S = kMaxThreads / GX;
+  if (GX > kMaxThreads - 32) return false;  // one warp of the CTA is the producer
+  int S = (kMaxThreads - 32) / GX;
   if (S > p.T_h) S = p.T_h;
-  const int rps = (p.T_h + S - 1) / S;
+  if (S > 16) S = 16;
+  g->GX = GX; g->S = S;
+  g->cwarps = (GX * S + 31) / 32;
+  g->threads = g->cwarps * 32 + 32;
+  // Row strips.  Threads of one warp should see the same "source rows moved" flags, otherwise the warp executes the
+  // refill path of two strips.  Strip boundaries in thread space are multiples of GX; where one falls inside a warp the
+  // two strips sharing that warp are started a multiple of the flag period apart (the flags of view v repeat every
+  // T_h / gcd(T_h, ho_v) rows), and the remaining rows are spread evenly.
+  int period = 1;
+  for (int v = 0; v < p.V; v++) {
+    int a = p.T_h, b = p.view[v].map.ho;
+    while (b) { int t = a % b; a = b; b = t; }
+    const int pv = p.view[v].same_h ? 1 : p.T_h / a;
+    int x = period, y = pv;
+    while (y) { int t = x % y; x = y; y = t; }
+    period = period / x * pv;
+  }
+  int bnd[17];
+  bool fixed[17];
+  for (int q = 0; q <= S; q++) { bnd[q] = (int)((long long)p.T_h * q / S); fixed[q] = (q == 0 || q == S); }
+  if (period > 1 && period * S <= p.T_h) {
+    for (int q = 1; q < S; q++) {
+      if ((q * GX) % 32 != 0) {  // strips q-1 and q share a warp
+        int snapped = (bnd[q] - bnd[q - 1] + period / 2) / period * period;
+        if (snapped < period) snapped = period;
+        bnd[q] = bnd[q - 1] + snapped;
+        fixed[q] = true;
+      } else if (fixed[q - 1]) {
+        // re-balance the free boundaries up to the next fixed one
+        int nxt = q;
+        while (!fixed[nxt] && ((nxt * GX) % 32 == 0) && nxt < S) nxt++;
+        (void)nxt;
+      }
+    }
+    // spread rows evenly between consecutive fixed boundaries
+    int q0 = 0;
+    for (int q = 1; q <= S; q++) {
+      if (!fixed[q]) continue;
+      for (int r = q0 + 1; r < q; r++) bnd[r] = bnd[q0] + (int)((long long)(bnd[q] - bnd[q0]) * (r - q0) / (q - q0));
+      q0 = q;
+    }
+  }
+  int rps = 0;
+  for (int q = 0; q < S; q++) {
+    if (bnd[q + 1] <= bnd[q]) return false;
+    g->strip_y0[q] = bnd[q];
+    if (bnd[q + 1] - bnd[q] > rps) rps = bnd[q + 1] - bnd[q];
+  }
+  g->strip_y0[S] = p.T_h;
   if (rps * 2 > 255) return false;  // packed 8-bit confusion counters
-  g->GX = GX; g->S = S; g->rows_per_strip = rps;
-  g->threads = (GX * S + 31) / 32 * 32;
-  if (g->threads < 64) g->threads = 64;
+  g->rows_per_strip = rps;
   int fl = 0;
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
