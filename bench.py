@@ -152,7 +152,7 @@ def run_ours(args):
     sizes = synthetic.view_sizes(T, SCALES)
     # synthetic inputs: a 1024-tile seeded block generated on the CPU (identical bits to what the oracle sees),
     # tiled up to N on the device so that one step streams 2.8 GB (>> 126 MB L2) through the kernel
-    base = synthetic.cfg2(N=min(N, 1024), T=T, C=C, scales=SCALES)
+    base = synthetic.cfg2(N=min(N, 1024), T=T, C=C, scales=SCALES, single_frac=args.single_frac)
     rep = (N + base["views"][0].shape[0] - 1) // base["views"][0].shape[0]
 
     def up(t):
@@ -287,6 +287,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=90.0, help="seconds of CPU work for the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--single-frac", type=float, default=0.4, help="fraction of single-label tiles (SURVEY.md 8(d) cfg 2: 0.4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

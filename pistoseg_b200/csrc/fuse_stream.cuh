@@ -114,6 +114,18 @@ __device__ __forceinline__ void top2(const float (&v)[C], int& bi, float& bv, fl
   }
 }
 
+// near tie / NaN / absurd magnitude / MULTIPLY mask: follow the reference operation by operation (kept out of line so
+// that the row loop's instruction footprint stays small)
+template <int C>
+__device__ __noinline__ void decide_pair_slow(const u64 (&acc)[C], uint32_t present_bits, const DecideCfg& cfg, bool ok0, bool ok1,
+                                              int& lab0, int& lab1) {
+  float a0[C], a1[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) unpack2(acc[c], a0[c], a1[c]);
+  if (!ok0) lab0 = pisto_decide<C>(a0, present_bits, cfg, false, nullptr);
+  if (!ok1) lab1 = pisto_decide<C>(a1, present_bits, cfg, false, nullptr);
+}
+
 // Labels of the two pixels of a packed pair from the undivided view sums acc[] (see pisto_decide in common.cuh for
 // the argument behind the fast path); madd2[c] is (0,0) for usable classes and (-inf,-inf) for classes masked out by
 // the tile's presence vector.
@@ -134,18 +146,11 @@ __device__ __forceinline__ void decide_pair(const u64 (&acc)[C], const u64 (&mad
   top2<C>(v1, lab1, bv1, sv1);
   const bool ok0 = fast_ok && (__fsub_rn(bv0, sv0) > __fmaf_rn(fabsf(bv0), 2.4e-7f, cfg.margin_abs)) && (fabsf(chk0) < 1e30f) && (bv0 > -1e9f);
   const bool ok1 = fast_ok && (__fsub_rn(bv1, sv1) > __fmaf_rn(fabsf(bv1), 2.4e-7f, cfg.margin_abs)) && (fabsf(chk1) < 1e30f) && (bv1 > -1e9f);
-  if (!(ok0 && ok1)) {  // near tie / NaN / absurd magnitude / MULTIPLY mask: follow the reference operation by operation
-    float a0[C], a1[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) unpack2(acc[c], a0[c], a1[c]);
-    if (!ok0) lab0 = pisto_decide<C>(a0, present_bits, cfg, false, nullptr);
-    if (!ok1) lab1 = pisto_decide<C>(a1, present_bits, cfg, false, nullptr);
-  }
+  if (!(ok0 && ok1)) decide_pair_slow<C>(acc, present_bits, cfg, ok0, ok1, lab0, lab1);
 }
 
-// F >= 0: bit 0 = bg given, 1 = gt + conf given, 2 = fused_out, 3 = in-kernel 32x32 export, 4 = label_out -- fixed at compile time so that
-// the per-row epilogue carries no pointer tests; F < 0: decided at run time (any combination).
-template <int C, int V, bool PROB, int F>
+// PAIRS: views 2k and 2k+1 (a scale and its flipped twin) share their row geometry -> one weight load / one flag test per pair.
+template <int C, int V, bool PROB, int F, bool PAIRS>
 __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __grid_constant__ FuseParams p,
                                                                      const __grid_constant__ StreamGeom g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -188,13 +193,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
     unsigned int f = 0;
     for (int v = 0; v < V; v++) {
       const ViewDev& vw = p.view[v];
-      unsigned int fl = 2;  // first row of a strip: load both source rows
+      unsigned int fl = 0;  // first row of a strip: both source rows are loaded before the row loop
       bool strip_start = false;
       for (int q = 0; q < g.S; q++) strip_start |= (y == g.strip_y0[q]);
       if (!strip_start) {
         const Lerp L = pisto_src_index(vw.scale_h, y, vw.map.ho, vw.same_h);
         const Lerp P = pisto_src_index(vw.scale_h, y - 1, vw.map.ho, vw.same_h);
-        fl = (P.i0 == L.i0 && P.i1 == L.i1) ? 0u : ((L.i0 == P.i1 && P.i1 == P.i0 + 1) ? 1u : 2u);
+        fl = (P.i0 == L.i0 && P.i1 == L.i1) ? 0u : 1u;  // up-sampling / same size: the pair moves down by exactly one row
       }
       f |= fl << (2 * v);
     }
@@ -327,6 +332,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
       float* lowp = need_low ? p.lowres_out + ((long long)n * C * p.low_h + low_first) * p.low_w : nullptr;
       int low_next = need_low ? low_first * p.low_fh + p.low_fh / 2 : 0x7fffffff;
       uint32_t rt = rowtab_s + 16u * V * ys, ro_a = rowoff_s + 8u * V * ys, fl_a = rowflags_s + 4u * ys;
+      // first row of the strip: load both bracketing source rows of every view (inside the loop rows only ever shift by one:
+      // the host routes view sets with ho > T_h, whose source rows can jump, to the block kernel)
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const int2 ro = lds_i2(ro_a + 8u * v);
+        load_h(v, vb[v] + ro.x, Ha[v]);
+        load_h(v, vb[v] + ro.y, Hb[v]);
+      }
       // byte masks are fetched two rows ahead of their use (HBM latency >> one row of arithmetic)
       unsigned int bg_c = 0, bg_n = 0, gt_c = 0, gt_n = 0;
       if (has_bg) {
@@ -348,23 +361,26 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
           if (has_bg) { bg_n = __ldg(reinterpret_cast<const unsigned short*>(bgp)); bgp += T_w; }
           if (do_conf) { gt_n = __ldg(reinterpret_cast<const unsigned short*>(gtp)); gtp += T_w; }
         }
-        if (flags) {  // the bracketing source rows of at least one view moved
+        if (flags) {  // the bracketing source rows of at least one view moved down by one
 #pragma unroll
           for (int v = 0; v < V; v++) {
-            const unsigned int f = (flags >> (2 * v)) & 3u;
-            if (f) {
-              const int2 ro = lds_i2(ro_a + 8u * v);
-              if (f == 2u) load_h(v, vb[v] + ro.x, Hb[v]);  // reload both (strip start / down-sampling views)
+            if (PAIRS && (v & 1)) continue;  // handled together with its twin
+            if ((flags >> (2 * v)) & 3u) {
 #pragma unroll
-              for (int c = 0; c < C; c++) Ha[v][c] = Hb[v][c];
-              load_h(v, vb[v] + ro.y, Hb[v]);
+              for (int vv = v; vv < v + (PAIRS ? 2 : 1); vv++) {
+                const int2 ro = lds_i2(ro_a + 8u * vv);
+#pragma unroll
+                for (int c = 0; c < C; c++) Ha[vv][c] = Hb[vv][c];
+                load_h(vv, vb[vv] + ro.y, Hb[vv]);
+              }
             }
           }
         }
         u64 acc[C];
+        ulonglong2 w;
 #pragma unroll
         for (int v = 0; v < V; v++) {
-          const ulonglong2 w = lds_u64x2(rt + 16u * v);
+          if (!(PAIRS && (v & 1))) w = lds_u64x2(rt + 16u * v);
           u64 u[C];
 #pragma unroll
           for (int c = 0; c < C; c++) u[c] = fma2(w.x, Ha[v][c], mul2(w.y, Hb[v][c]));
@@ -610,11 +626,11 @@ static bool make_geom(const pisto_ctx* h, const FuseParams& p, StreamGeom* g) {
   return off <= h->smem_optin - 1024;
 }
 
-template <int C, int V, bool PROB, int F>
+template <int C, int V, bool PROB, int F, bool PAIRS>
 int launch_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   StreamGeom g;
   if (!make_geom(h, p, &g)) return PISTO_OK;  // not launched: caller falls back
-  auto kern = fuse_stream_kernel<C, V, PROB, F>;
+  auto kern = fuse_stream_kernel<C, V, PROB, F, PAIRS>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
@@ -633,14 +649,32 @@ static inline int pisto_stream_flags(const FuseParams& p) {
   return (p.bg ? 1 : 0) | ((p.conf && p.gt) ? 2 : 0) | (p.fused_out ? 4 : 0) | ((p.lowres_out && p.low_fh > 0) ? 8 : 0) | (p.label_out ? 16 : 0);
 }
 
+// views 2k / 2k+1 share their row geometry (a scale and its flipped twin)?
+static inline bool pisto_stream_pairs(const FuseParams& p) {
+  if (p.V < 2 || (p.V & 1)) return false;
+  for (int v = 0; v < p.V; v += 2)
+    if (p.view[v].map.ho != p.view[v + 1].map.ho) return false;
+  return true;
+}
+
 // one (C, V) family: specialised feature masks for the BASELINE configs, run-time flags for everything else
 template <int C, int V>
 static int pisto_launch_stream_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
-  if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) return launch_cv<C, V, true, -1>(h, p, st, launched);
+  for (int v = 0; v < p.V; v++)
+    if (p.view[v].map.ho >= p.T_h) return PISTO_OK;  // same-size / down-sampling rows: the source-row pair does not move by exactly one -> block kernel
+  if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) return launch_cv<C, V, true, -1, false>(h, p, st, launched);
+  if ((V % 2 == 0) && pisto_stream_pairs(p)) {
+    switch (pisto_stream_flags(p)) {
+      case 25: return launch_cv<C, V, false, 25, (V % 2 == 0)>(h, p, st, launched);
+      case 19: return launch_cv<C, V, false, 19, (V % 2 == 0)>(h, p, st, launched);
+      case 18: return launch_cv<C, V, false, 18, (V % 2 == 0)>(h, p, st, launched);
+      default: return launch_cv<C, V, false, -1, (V % 2 == 0)>(h, p, st, launched);
+    }
+  }
   switch (pisto_stream_flags(p)) {
-    case 25: return launch_cv<C, V, false, 25>(h, p, st, launched);  // bg + labels + 32x32        (config 2)
-    case 19: return launch_cv<C, V, false, 19>(h, p, st, launched);  // bg + gt/conf + labels      (config 1)
-    case 18: return launch_cv<C, V, false, 18>(h, p, st, launched);  // gt/conf + labels           (config 3, mIoUMask.forward)
-    default: return launch_cv<C, V, false, -1>(h, p, st, launched);
+    case 25: return launch_cv<C, V, false, 25, false>(h, p, st, launched);  // bg + labels + 32x32        (config 2)
+    case 19: return launch_cv<C, V, false, 19, false>(h, p, st, launched);  // bg + gt/conf + labels      (config 1)
+    case 18: return launch_cv<C, V, false, 18, false>(h, p, st, launched);  // gt/conf + labels           (config 3, mIoUMask.forward)
+    default: return launch_cv<C, V, false, -1, false>(h, p, st, launched);
   }
 }

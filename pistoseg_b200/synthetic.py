@@ -61,11 +61,11 @@ def cfg1(N=256, T=224, C=3):
     return dict(views=views, codes=codes, T=T, C=C, gt=gt, bg=(gt == C).to(torch.uint8), present=None)
 
 
-def cfg2(N=1024, T=224, C=3, scales=(0.75, 1.0, 1.25)):
+def cfg2(N=1024, T=224, C=3, scales=(0.75, 1.0, 1.25), single_frac=0.4):
     """BASELINE config 2: pseudo-mask inference, V=6 (3 scales x flip), present vector, bg, 32x32 logits export."""
     views, codes = make_views(N, C, view_sizes(T, scales), 2001)
     gt = make_gt(N, T, C, 2002)
-    return dict(views=views, codes=codes, T=T, C=C, gt=None, bg=(gt == C).to(torch.uint8), present=make_present(N, C, 2003))
+    return dict(views=views, codes=codes, T=T, C=C, gt=None, bg=(gt == C).to(torch.uint8), present=make_present(N, C, 2003, single_frac))
 
 
 def cfg3(N=1000, T=224, C=4, scales=(0.75, 1.0, 1.25)):
