@@ -35,9 +35,9 @@ struct MosaicParams {
 
 __device__ __forceinline__ int reflect101(int p, int n) {
   if (n == 1) return 0;
-  int period = 2 * (n - 1);
+  const int period = 2 * (n - 1);
   p = p < 0 ? -p : p;
-  p %= period;
+  if (p >= period) p %= period;  // rare: overshoot by more than one image size
   return p >= n ? period - p : p;
 }
 
@@ -53,24 +53,31 @@ __device__ __forceinline__ int cv_round(double v) {
 
 struct SrcPix { long long off; int t; };  // pixel offset into the pool (pool_off[t] + ty*tw + tx), tile id
 
-// composite coordinate (after flip) -> pool pixel
+// composite coordinate (after flip) -> pool pixel.  PS > 0: patch size known at compile time (division by constant).
+template <int PS>
 __device__ __forceinline__ SrcPix composite_src(const MosaicParams& p, const pisto_mosaic_cell_t* cells_q, int flip, int y, int x) {
+  const int ps = PS > 0 ? PS : p.ps;
   if (flip & 1) y = p.S - 1 - y;   // cv2.flip code 0 / -1: rows reversed
   if (flip & 2) x = p.S - 1 - x;   // cv2.flip code 1 / -1: cols reversed
-  const int cr = y / p.ps, cc = x / p.ps;
-  const int iy = y - cr * p.ps, ix = x - cc * p.ps;
+  const int cr = y / ps, cc = x / ps;
+  const int iy = y - cr * ps, ix = x - cc * ps;
   const pisto_mosaic_cell_t cell = cells_q[cr * p.pn + cc];
-  const int th = p.pool_hw[2 * cell.tile], tw = p.pool_hw[2 * cell.tile + 1];
-  const int pad_t = th < p.ps ? (int)((p.ps - th) / 2.0) : 0;
-  const int pad_l = tw < p.ps ? (int)((p.ps - tw) / 2.0) : 0;
-  const int ty = reflect101(cell.cy + iy - pad_t, th);
-  const int tx = reflect101(cell.cx + ix - pad_l, tw);
+  const int2 hw = __ldg(reinterpret_cast<const int2*>(p.pool_hw) + cell.tile);
+  const int th = hw.x, tw = hw.y;
+  int ty = cell.cy + iy, tx = cell.cx + ix;
+  if (th < ps || tw < ps) {  // PadIfNeeded: centred REFLECT_101 pad (rare)
+    const int pad_t = th < ps ? (ps - th) >> 1 : 0;   // int((ps - th) / 2.0)
+    const int pad_l = tw < ps ? (ps - tw) >> 1 : 0;
+    ty = reflect101(ty - pad_t, th);
+    tx = reflect101(tx - pad_l, tw);
+  }
   SrcPix s;
   s.t = cell.tile;
   s.off = p.pool_off[cell.tile] + (long long)ty * tw + tx;
   return s;
 }
 
+template <int PS>
 __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant__ MosaicParams p) {
   const int S = p.S;
   const int groups_per_row = S / 4;
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
       const int xc = (X >= sw ? X - sw : X) + qd->crop_x;
       const int flip = qd->flip;
       if (!qd->warp) {
-        SrcPix s = composite_src(p, cells_q, flip, yc, xc);
+        SrcPix s = composite_src<PS>(p, cells_q, flip, yc, xc);
         const uint8_t* px = p.pool_img + 3 * s.off;
         img_bytes[3 * k + 0] = px[0]; img_bytes[3 * k + 1] = px[1]; img_bytes[3 * k + 2] = px[2];
         unsigned int m = p.pool_label[s.t];
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
         {  // INTER_NEAREST (mask): round_delta = AB_SCALE / 2
           const int sx = sat_short((X0b + 512 + adelta) >> AB_BITS);
           const int sy = sat_short((Y0b + 512 + bdelta) >> AB_BITS);
-          SrcPix s = composite_src(p, cells_q, flip, reflect101(sy, S), reflect101(sx, S));
+          SrcPix s = composite_src<PS>(p, cells_q, flip, reflect101(sy, S), reflect101(sx, S));
           unsigned int m = p.pool_label[s.t];
           if (p.pool_bg && p.pool_bg[s.off] > 0) m = p.bg_label;
           mask_bytes[k] = m;
@@ -124,10 +131,10 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
           int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
           if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
           const int x0r = reflect101(sx, S), x1r = reflect101(sx + 1, S), y0r = reflect101(sy, S), y1r = reflect101(sy + 1, S);
-          const uint8_t* p00 = p.pool_img + 3 * composite_src(p, cells_q, flip, y0r, x0r).off;
-          const uint8_t* p01 = p.pool_img + 3 * composite_src(p, cells_q, flip, y0r, x1r).off;
-          const uint8_t* p10 = p.pool_img + 3 * composite_src(p, cells_q, flip, y1r, x0r).off;
-          const uint8_t* p11 = p.pool_img + 3 * composite_src(p, cells_q, flip, y1r, x1r).off;
+          const uint8_t* p00 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y0r, x0r).off;
+          const uint8_t* p01 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y0r, x1r).off;
+          const uint8_t* p10 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y1r, x0r).off;
+          const uint8_t* p11 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y1r, x1r).off;
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
             int v = (int)p00[ch] * w00 + (int)p01[ch] * w01 + (int)p10[ch] * w10 + (int)p11[ch] * w11;
@@ -168,7 +175,13 @@ extern "C" int pisto_mosaic_gather(pisto_handle_t h, const uint8_t* pool_img, co
   long long grid = (total + kThreads - 1) / kThreads;
   long long cap = (long long)h->sm_count * 16;
   if (grid > cap) grid = cap;
-  mosaic_kernel<<<(int)grid, kThreads, 0, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (patch_size) {
+    case 32: mosaic_kernel<32><<<(int)grid, kThreads, 0, st>>>(p); break;
+    case 56: mosaic_kernel<56><<<(int)grid, kThreads, 0, st>>>(p); break;
+    case 112: mosaic_kernel<112><<<(int)grid, kThreads, 0, st>>>(p); break;
+    default: mosaic_kernel<0><<<(int)grid, kThreads, 0, st>>>(p); break;
+  }
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   return PISTO_OK;

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Secondary measurements (one JSON object per line -> gpurun_out/bench_all.jsonl): every BASELINE config and every kernel
+of the library, device-resident, CUDA events, inputs larger than L2.  Not the contract line (that is bench.py)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pistoseg_b200 import _lib, mosaic, ops, synthetic  # noqa: E402
+from pistoseg_b200._lib import DECIDE_RAW, DECIDE_SOFTMAX, FUSE_PROB_MEAN, IMPL_GENERIC, MASK_FILL  # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAK = 6535.4
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+out_path = os.path.join(ROOT, "gpurun_out", "bench_all.jsonl")
+os.makedirs(os.path.dirname(out_path), exist_ok=True)
+fout = open(out_path, "w")
+
+
+def timeit(fn, steps=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def emit(name, units, unit_name, ms, bytes_per_unit, **extra):
+    rate = units / (ms * 1e-3)
+    gbs = rate * bytes_per_unit / 1e9
+    rec = dict(name=name, value=rate, unit=f"{unit_name}/s", ms=ms, bytes_per_unit=bytes_per_unit, achieved_gbs=gbs, hbm_frac=gbs / PEAK, **extra)
+    print(json.dumps(rec)); fout.write(json.dumps(rec) + "\n"); fout.flush()
+
+
+def rep(t, n):
+    r = (n + t.shape[0] - 1) // t.shape[0]
+    return t.to(dev).repeat((r,) + (1,) * (t.dim() - 1))[:n].contiguous()
+
+
+def fuse_case(name, cfg, N, steps=20, **kw):
+    views = [rep(v, N) for v in cfg["views"]]
+    args = dict(present=rep(cfg["present"], N) if cfg.get("present") is not None else None,
+                bg=rep(cfg["bg"], N) if cfg.get("bg") is not None else None,
+                gt=rep(cfg["gt"], N) if cfg.get("gt") is not None else None)
+    T, C = cfg["T"], cfg["C"]
+    conf = ops.new_confusion(C, dev) if args["gt"] is not None else None
+    fn = lambda: ops.fuse_argmax_confusion(views, cfg["codes"], (T, T), conf=conf, **args, **kw)
+    ms = timeit(fn, steps)
+    b = 4 * C * sum(v.shape[2] * v.shape[3] for v in views) + T * T * (1 + (args["bg"] is not None) + (args["gt"] is not None)) + (4 * C * 1024 if kw.get("lowres") else 0)
+    emit(name, N, "tiles", ms, b, views=[int(v.shape[2]) for v in views])
+
+
+# ---- fused path, every BASELINE config ------------------------------------------------------------------------------
+fuse_case("cfg1 single stride-8 view, bg+gt+labels+confusion (C=3)", synthetic.cfg1(N=1024), 16384, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)
+fuse_case("cfg2 pseudo-mask: 3 scales x flip, present, bg, labels, 32x32 (C=3)", synthetic.cfg2(N=1024), 16384, mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+fuse_case("cfg2 all multi-label tiles", synthetic.cfg2(N=1024, single_frac=0.0), 16384, mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+fuse_case("cfg3 BCSS: 3 scales x flip, gt, labels, confusion (C=4)", synthetic.cfg3(N=1000), 10000, decide=DECIDE_SOFTMAX)
+fuse_case("cfg2 PROB_MEAN fusion (softmax per view)", synthetic.cfg2(N=1024), 8192, fuse_mode=FUSE_PROB_MEAN, decide=DECIDE_RAW, bg_match=1, bg_label=3)
+for T, N in ((512, 512), (1024, 128)):
+    fuse_case(f"cfg5 large tile T={T}: 5 scales x flip, gt, labels, confusion (C=4)", synthetic.cfg5(N=8, T=T), N, steps=5, decide=DECIDE_SOFTMAX)
+# reference-literal Mode F: 8 full-resolution d4 views
+from pistoseg_b200 import tta  # noqa: E402
+g = torch.Generator().manual_seed(1)
+N = 256
+views = [torch.randn((N, 3, 224, 224), generator=g, dtype=torch.float32).to(dev) for _ in range(8)]
+codes = [tta.deaug_code(h, a) for h, a in tta.aliases.d4_transform()]
+bg = (torch.rand((N, 224, 224), generator=g) < 0.15).to(torch.uint8).to(dev)
+pres = synthetic.make_present(N, 3, 5).to(dev)
+ms = timeit(lambda: ops.fuse_argmax_confusion(views, codes, (224, 224), mask_mode=MASK_FILL, present=pres, bg=bg, bg_match=1, bg_label=3, lowres=(32, 32)), 5)
+emit("modeF: 8 full-res d4 views (ttach literal), present, bg, labels, 32x32", N, "tiles", ms, 8 * 3 * 224 * 224 * 4 + 2 * 224 * 224 + 12288)
+# mIoUMask.forward shape: single full-res view + gt -> confusion (loss.py:55-67)
+x = torch.randn((1024, 3, 224, 224), generator=g).to(dev); gt = torch.randint(0, 4, (1024, 224, 224), generator=g, dtype=torch.uint8).to(dev)
+conf = ops.new_confusion(3, dev)
+ms = timeit(lambda: ops.fuse_argmax_confusion([x], [0], (224, 224), gt=gt, conf=conf, want_labels=False), 10)
+emit("mIoUMask.forward: softmax+argmax+confusion of full-res logits (C=3)", 1024, "tiles", ms, 3 * 224 * 224 * 4 + 224 * 224)
+
+# ---- confusion kernel -----------------------------------------------------------------------------------------------
+n = 10_000 * 224 * 224
+pred = torch.randint(0, 4, (n,), dtype=torch.uint8, device=dev); gtb = torch.randint(0, 5, (n,), dtype=torch.uint8, device=dev)
+conf = ops.new_confusion(4, dev)
+ms = timeit(lambda: ops.confusion_accumulate(pred, gtb, conf), 20)
+emit("confusion_accumulate 10k BCSS tiles (C=4)", 10000, "tiles", ms, 2 * 224 * 224)
+del pred, gtb
+# ---- bilinear resize ------------------------------------------------------------------------------------------------
+x = torch.randn((8192, 3, 28, 28), device=dev)
+ms = timeit(lambda: ops.upsample_bilinear(x, (224, 224)), 10)
+emit("upsample_bilinear f32 28->224 (C=3)", 8192, "tiles", ms, 3 * 4 * (28 * 28 + 224 * 224))
+x64 = torch.randn((3, 2000, 2500), device=dev, dtype=torch.float64)
+ms = timeit(lambda: ops.upsample_bilinear(x64, (1600, 2000)), 10)
+emit("upsample_bilinear f64 2000x2500 -> 1600x2000 (C=3)", 1, "images", ms, 3 * 8 * (2000 * 2500 + 1600 * 2000))
+# ---- mosaic ---------------------------------------------------------------------------------------------------------
+rng = np.random.default_rng(0)
+P = 2048
+imgs = [rng.integers(0, 256, (224, 224, 3), dtype=np.uint8) for _ in range(64)]
+imgs = [imgs[i % 64] for i in range(P)]
+bgs = [(rng.random((224, 224)) < 0.1).astype(np.uint8) * 255 for _ in range(64)]
+bgs = [bgs[i % 64] for i in range(P)]
+pool = mosaic.TilePool(imgs, rng.integers(0, 3, P).astype(np.uint8), bgs, device=dev)
+for pn, ps in ((4, 56), (2, 112), (7, 32)):
+    planner = mosaic.MosaicPlanner(pool, pn, ps, reject_bg=False)
+    t0 = time.perf_counter(); plans, cells = planner.plans(range(512)); plan_s = time.perf_counter() - t0
+    reps = 16
+    plans = np.tile(plans, reps); cells = np.tile(cells, (reps, 1, 1))
+    pl = torch.from_numpy(plans.view(np.uint8).reshape(-1)).to(dev); ce = torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(dev)
+    ms = timeit(lambda: ops.mosaic_gather(pool.dev, pl, ce, pn, ps, 3), 5)
+    emit(f"mosaic_gather {pn}x{ps} (224x224 image+mask, 80% warped quadrants)", len(plans), "mosaics", ms, 2 * (224 * 224 * 4), host_plan_us_per_mosaic=plan_s / 512 * 1e6)
+fout.close()
