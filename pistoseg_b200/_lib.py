@@ -16,7 +16,7 @@ MAX_CLASSES = 8
 FUSE_LOGIT_MEAN, FUSE_PROB_MEAN = 0, 1
 MASK_NONE, MASK_FILL, MASK_NEG_INF, MASK_MULTIPLY = 0, 1, 2, 3
 DECIDE_SOFTMAX, DECIDE_RAW = 0, 1
-IMPL_AUTO, IMPL_GENERIC, IMPL_STREAM = 0, 1, 2
+IMPL_AUTO, IMPL_GENERIC, IMPL_STREAM, IMPL_FILTER2, IMPL_FILTER4 = 0, 1, 2, 3, 4
 
 
 class PistoError(RuntimeError):

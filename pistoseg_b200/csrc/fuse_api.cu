@@ -75,7 +75,16 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
   cudaStream_t st = (cudaStream_t)stream;
   PISTO_CUDA(cudaSetDevice(h->device));
   bool launched = false;
-  if (a->impl != 1) {
+  if (a->impl == 0 || a->impl == 3 || a->impl == 4) {
+    rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : a->impl - 2, &launched);
+    if (rc != PISTO_OK) return rc;
+    if (!launched && a->impl != 0) {
+      pisto_set_error("pisto_fuse_argmax_confusion: impl=%d (filtered streaming kernel) has no instantiation for C=%d V=%d T=%dx%d with these options",
+                      a->impl, p.C, p.V, p.T_h, p.T_w);
+      return PISTO_ERR_UNSUPPORTED;
+    }
+  }
+  if (!launched && a->impl != 1) {
     rc = pisto_launch_fuse_stream(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched) {

@@ -1,0 +1,154 @@
+"""The filtered streaming kernel (fuse_filter.cuh) decides labels from interpolated class-difference fields and falls back
+to the exact evaluation below an error-bound margin: its labels / confusion matrices must equal the exact kernels' (and the
+oracle's) bit for bit, its 32x32 logit export must be bit-exact, on ordinary and on adversarial inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import confusion as oconf
+from oracle import fuse as ofuse
+from pistoseg_b200 import ops, synthetic
+from pistoseg_b200._lib import (DECIDE_RAW, DECIDE_SOFTMAX, IMPL_FILTER2, IMPL_FILTER4, IMPL_GENERIC, IMPL_STREAM, MASK_FILL,
+                                MASK_NEG_INF, MASK_NONE)
+
+pytestmark = pytest.mark.gpu
+FILTERS = [IMPL_FILTER2, IMPL_FILTER4]
+
+
+def run(cfg, cuda, impl, **kw):
+    views = [v.to(cuda) for v in cfg["views"]]
+    return ops.fuse_argmax_confusion(views, cfg["codes"], (cfg["T"], cfg["T"]), impl=impl,
+                                     present=cfg.get("present"), bg=cfg.get("bg"), gt=cfg.get("gt"), **kw)
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_cfg2_labels_and_lowres(cuda, impl):
+    cfg = synthetic.cfg2(N=96)
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+    out = run(cfg, cuda, impl, **kw)
+    ref = run(cfg, cuda, IMPL_STREAM, **kw)
+    assert torch.equal(out["labels"], ref["labels"])
+    assert torch.equal(out["lowres"], ref["lowres"])
+    fused = ofuse.fuse_views(cfg["views"], cfg["codes"], (224, 224))
+    assert torch.equal(out["lowres"].cpu(), ofuse.lowres_32(fused))
+    lab = ofuse.pseudo_masks(fused, cfg["present"].numpy(), cfg["bg"].numpy())
+    assert (out["labels"].cpu().numpy() == lab).mean() >= 0.9999
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_cfg2_all_multi_label_no_lowres(cuda, impl):
+    cfg = synthetic.cfg2(N=48, single_frac=0.0)
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)
+    out = run(cfg, cuda, impl, **kw)
+    ref = run(cfg, cuda, IMPL_GENERIC, **kw)
+    assert torch.equal(out["labels"], ref["labels"])
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_cfg1_confusion(cuda, impl):
+    cfg = synthetic.cfg1(N=40)
+    kw = dict(mask_mode=MASK_NONE, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)
+    out = run(cfg, cuda, impl, **kw)
+    ref = run(cfg, cuda, IMPL_STREAM, **kw)
+    assert torch.equal(out["labels"], ref["labels"])
+    assert torch.equal(out["conf"], ref["conf"])
+    fused = ofuse.fuse_views(cfg["views"], cfg["codes"], (224, 224))
+    pred = ofuse.miou_pred(fused).numpy()
+    cm = sum(oconf.generate_matrix(pred[n], cfg["gt"][n].numpy(), 3) for n in range(pred.shape[0]))
+    assert np.array_equal(out["conf"].cpu().numpy(), cm)
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_cfg3_bcss(cuda, impl):
+    cfg = synthetic.cfg3(N=40)
+    out = run(cfg, cuda, impl, decide=DECIDE_SOFTMAX)
+    ref = run(cfg, cuda, IMPL_STREAM, decide=DECIDE_SOFTMAX)
+    assert torch.equal(out["labels"], ref["labels"])
+    assert torch.equal(out["conf"], ref["conf"])
+    # conf only (no label output)
+    out2 = run(cfg, cuda, impl, decide=DECIDE_RAW, want_labels=False)
+    ref2 = run(cfg, cuda, IMPL_GENERIC, decide=DECIDE_RAW, want_labels=False)
+    assert torch.equal(out2["conf"], ref2["conf"])
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_near_ties_go_through_the_exact_pass(cuda, impl):
+    """Class scores that differ by ~1e-6 .. 1e-3 almost everywhere: most pixels fail the margin test, the queue overflows on
+    some tiles and not on others; the labels must still be the exact kernel's."""
+    g = torch.Generator().manual_seed(77)
+    N = 24
+    cfg = synthetic.cfg2(N=N, single_frac=0.0)
+    scale = torch.logspace(-7, -2, N).view(N, 1, 1, 1)
+    views = []
+    for v in cfg["views"]:
+        base = v[:, :1].clone()
+        views.append(torch.cat([base, base + torch.randn(v[:, 1:].shape, generator=g) * scale], 1).contiguous())
+    cfg["views"] = views
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+    out = run(cfg, cuda, impl, **kw)
+    ref = run(cfg, cuda, IMPL_GENERIC, **kw)
+    assert torch.equal(out["labels"], ref["labels"])
+    assert torch.equal(out["lowres"], ref["lowres"])
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_exact_ties_constant_and_rounded_logits(cuda, impl):
+    cfg = synthetic.cfg1(N=12)
+    v = torch.round(cfg["views"][0] * 2) / 2
+    v[0] = 0.0          # all classes tie everywhere: lowest index wins
+    v[1] = 1.5
+    cfg["views"] = [v]
+    for decide in (DECIDE_RAW, DECIDE_SOFTMAX):
+        out = run(cfg, cuda, impl, decide=decide, bg_match=255)
+        ref = run(cfg, cuda, IMPL_GENERIC, decide=decide, bg_match=255)
+        assert torch.equal(out["labels"], ref["labels"])
+        assert torch.equal(out["conf"], ref["conf"])
+    assert int(out["labels"][0].max()) == 0
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_non_finite_and_huge_logits(cuda, impl):
+    cfg = synthetic.cfg3(N=10)
+    cfg["views"] = [v.clone() for v in cfg["views"]]
+    cfg["views"][0][1, 2, 3, 4] = float("nan")
+    cfg["views"][2][2, 0, 5, 6] = float("inf")
+    cfg["views"][3][3, 1, 7, 7] = float("-inf")
+    cfg["views"][1][4] *= 1e20
+    cfg["views"][5][5] *= 1e-20
+    for decide in (DECIDE_RAW, DECIDE_SOFTMAX):
+        out = run(cfg, cuda, impl, decide=decide)
+        ref = run(cfg, cuda, IMPL_GENERIC, decide=decide)
+        assert torch.equal(out["labels"], ref["labels"])
+        assert torch.equal(out["conf"], ref["conf"])
+
+
+@pytest.mark.parametrize("impl", FILTERS)
+def test_presence_edge_cases(cuda, impl):
+    cfg = synthetic.cfg2(N=16, single_frac=0.0)
+    pres = cfg["present"].clone()
+    pres[0] = 0                                   # empty presence vector
+    pres[1] = torch.tensor([0, 0, 1])             # single class
+    pres[2] = torch.tensor([1, 1, 1])
+    pres[3] = torch.tensor([0, 1, 1])
+    cfg["present"] = pres
+    for mask in (MASK_FILL, MASK_NEG_INF):
+        for decide in (DECIDE_RAW, DECIDE_SOFTMAX):
+            kw = dict(mask_mode=mask, decide=decide, bg_match=1, bg_label=3, lowres=(32, 32))
+            out = run(cfg, cuda, impl, **kw)
+            ref = run(cfg, cuda, IMPL_GENERIC, **kw)
+            assert torch.equal(out["labels"], ref["labels"]), (mask, decide)
+            assert torch.equal(out["lowres"], ref["lowres"])
+
+
+def test_auto_dispatch_uses_the_filter_kernel_and_odd_shapes_fall_back(cuda):
+    cfg = synthetic.cfg2(N=20)
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+    a = run(cfg, cuda, 0, **kw)
+    b = run(cfg, cuda, IMPL_FILTER4, **kw)
+    assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["lowres"], b["lowres"])
+    # a view set the filter kernel has no instantiation for (V = 3) still works through the other kernels
+    g = torch.Generator().manual_seed(3)
+    views = [torch.randn((4, 3, h, h), generator=g) for h in (14, 28, 42)]
+    out = ops.fuse_argmax_confusion([v.to(cuda) for v in views], [0, 0, 0], (224, 224), decide=DECIDE_RAW)
+    ref = ops.fuse_argmax_confusion([v.to(cuda) for v in views], [0, 0, 0], (224, 224), decide=DECIDE_RAW, impl=IMPL_GENERIC)
+    assert torch.equal(out["labels"], ref["labels"])
