@@ -34,7 +34,8 @@
 
 namespace {
 
-constexpr int kFMaxThreads = 448;
+constexpr int kFMaxThreads = 512;
+constexpr int kFAux = 2;  // warps that evaluate the 32x32 logit export concurrently with the row loop
 constexpr int kFQueueCap = 1024;
 constexpr int kFMaxGroups = 4;
 
@@ -46,13 +47,15 @@ struct FilterGeom {
   int plane_bytes[PISTO_MAX_VIEWS];    // h*w*4
   int vbase[PISTO_MAX_VIEWS], vrow[PISTO_MAX_VIEWS], vcol[PISTO_MAX_VIEWS];  // byte address of de-augmented (i, j): vbase + i*vrow + j*vcol
   int group_of[PISTO_MAX_VIEWS];
+  int first_in_group[PISTO_MAX_VIEWS];
   int buf_floats;
   int g_ho[kFMaxGroups], g_wo[kFMaxGroups], g_same_w[kFMaxGroups];
   float g_scale_h[kFMaxGroups], g_scale_w[kFMaxGroups];
   int g_ybytes[kFMaxGroups];           // byte offset of group g's first difference map inside the Y area
   int g_mapbytes[kFMaxGroups];         // ho*wo*4
+  unsigned int g_inv[kFMaxGroups];     // ceil(2^32 / wo): idx / wo == umulhi(idx, inv) for idx < 2^16
   float tau_coef, tau_abs;             // tau = V * max|x| * tau_coef + tau_abs
-  int ctl_off, rowtab_off, rowoff_off, cola_off, colb_off, lowrow_off, lowcol_off, ymap_off, queue_off, views_off;
+  int ctl_off, rowtab_off, rowoff_off, cola_off, colb_off, lowrow_off, lowcol_off, ymap_off, queue_off, lab_off, views_off;
   int smem_bytes;
   int* counter;
 };
@@ -63,10 +66,12 @@ struct FCtl {
   int tile[2];
   unsigned int maxbits[2];  // max |x| of the tile (IEEE bits; NaN > Inf > finite), slot = tile parity
   unsigned int qcount[2];   // uncertain pixels queued by the row loop
+  unsigned int lownext[2];  // next low-resolution row of the logit export to be claimed (any warp may claim)
   unsigned int hist[64];
 };
 
 // label among cls[0..K] from the difference candidates (0, d[0] .. d[K-1]); returns whether the lead exceeds tau
+// (used on the rare path only: the row loop decides through sign masks)
 template <int K, int C>
 __device__ __forceinline__ bool decide_diff(const float (&d)[K], const int (&cls)[C], float tau, int& lab) {
   float bv = fmaxf(0.f, d[0]), sv = fminf(0.f, d[0]);
@@ -98,12 +103,113 @@ template <int NP> __device__ __forceinline__ void stg_px(uint8_t* q, unsigned in
   if (NP == 2) *reinterpret_cast<unsigned int*>(q) = v;
   else *reinterpret_cast<unsigned short*>(q) = (unsigned short)v;
 }
+template <int NP> __device__ __forceinline__ void sts_px(uint32_t a, unsigned int v) {
+  if (NP == 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+  else asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+
+// byte j of the result = 0xff if a[j] is negative (PRMT replicates the sign bit of the selected byte when bit 3 of the
+// selector nibble is set); NP == 1: only bytes 0 and 1 are meaningful
+template <int NP> __device__ __forceinline__ unsigned int negmask(const float (&a)[2 * NP]) {
+  unsigned int t01, t23, r;
+  asm("prmt.b32 %0, %1, %2, 0x00fb;" : "=r"(t01) : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])));
+  if (NP == 1) return t01;
+  asm("prmt.b32 %0, %1, %2, 0x00fb;" : "=r"(t23) : "r"(__float_as_uint(a[2 * NP - 2])), "r"(__float_as_uint(a[2 * NP - 1])));
+  asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(t01), "r"(t23));
+  return r;
+}
+template <int N> __device__ __forceinline__ float minabs(const float (&a)[N]) {
+  float m = fabsf(a[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) m = fminf(m, fabsf(a[i]));
+  return m;
+}
+
+// Labels of the thread's 2*NP pixels from the packed difference fields acc[k][q] (pixel pair q, candidate k+1 minus
+// candidate 0).  The order of the candidates (0, D_1 .. D_K) is read off the SIGNS of the D_k and of their pairwise
+// differences; the result is trusted (return value) only when every one of those quantities is further than tau from
+// zero, which implies the best candidate leads every other one by more than tau.  c4[k] = 0x01010101 * cls[k].
+template <int K, int NP>
+__device__ __forceinline__ bool labels_from_diffs(const u64 (&acc)[K][NP], const unsigned int (&c4)[4], float tau, unsigned int& lab4) {
+  float d[K][2 * NP];
+#pragma unroll
+  for (int k = 0; k < K; k++)
+#pragma unroll
+    for (int q = 0; q < NP; q++) unpack2(acc[k][q], d[k][2 * q], d[k][2 * q + 1]);
+  float mn;
+  if (K == 1) {
+    const unsigned int n1 = negmask<NP>(d[0]);
+    lab4 = (c4[0] & n1) | (c4[1] & ~n1);
+    mn = minabs(d[0]);
+  } else if (K == 2) {
+    float e12[2 * NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) unpack2(sub2(acc[0][q], acc[K > 1 ? 1 : 0][q]), e12[2 * q], e12[2 * q + 1]);
+    const unsigned int n1 = negmask<NP>(d[0]), n2 = negmask<NP>(d[K > 1 ? 1 : 0]), n12 = negmask<NP>(e12);
+    const unsigned int m0 = n1 & n2, m1 = ~n1 & ~n12;
+    lab4 = (c4[0] & m0) | (c4[1] & m1) | (c4[2] & ~(m0 | m1));
+    mn = fminf(fminf(minabs(d[0]), minabs(d[K > 1 ? 1 : 0])), minabs(e12));
+  } else {
+    float e12[2 * NP], e13[2 * NP], e23[2 * NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      unpack2(sub2(acc[0][q], acc[K > 1 ? 1 : 0][q]), e12[2 * q], e12[2 * q + 1]);
+      unpack2(sub2(acc[0][q], acc[K > 2 ? 2 : 0][q]), e13[2 * q], e13[2 * q + 1]);
+      unpack2(sub2(acc[K > 1 ? 1 : 0][q], acc[K > 2 ? 2 : 0][q]), e23[2 * q], e23[2 * q + 1]);
+    }
+    const unsigned int n1 = negmask<NP>(d[0]), n2 = negmask<NP>(d[K > 1 ? 1 : 0]), n3 = negmask<NP>(d[K > 2 ? 2 : 0]);
+    const unsigned int n12 = negmask<NP>(e12), n13 = negmask<NP>(e13), n23 = negmask<NP>(e23);
+    const unsigned int m0 = n1 & n2 & n3, m1 = ~n1 & ~n12 & ~n13, m2 = ~n2 & n12 & ~n23;
+    lab4 = (c4[0] & m0) | (c4[1] & m1) | (c4[2] & m2) | (c4[3] & ~(m0 | m1 | m2));
+    mn = fminf(fminf(fminf(minabs(d[0]), minabs(d[K > 1 ? 1 : 0])), fminf(minabs(d[K > 2 ? 2 : 0]), minabs(e12))), fminf(minabs(e13), minabs(e23)));
+  }
+  return mn > tau;
+}
+
+// rare path: which of the thread's pixels really fail the lead test (top-2 gap of the candidates <= tau)
+template <int K, int NP, int C>
+__device__ __forceinline__ unsigned int uncertain_mask(const u64 (&acc)[K][NP], const int (&cls)[C], float tau) {
+  unsigned int unc = 0;
+#pragma unroll
+  for (int q = 0; q < NP; q++) {
+    float d0[K], d1[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) unpack2(acc[k][q], d0[k], d1[k]);
+    int l;
+    if (!decide_diff<K, C>(d0, cls, tau, l)) unc |= 1u << (2 * q);
+    if (!decide_diff<K, C>(d1, cls, tau, l)) unc |= 2u << (2 * q);
+  }
+  return unc;
+}
+
+// packed 8-bit confusion counters (two 64-bit registers hold C*C <= 16 bins)
+__device__ __forceinline__ void count_bin(u64& lo, u64& hi, unsigned int bn, unsigned int times) {
+  const u64 inc = (u64)times << (8 * (bn & 7));
+  if (bn < 8) lo += inc; else hi += inc;
+}
+// 4 pixels: ground truth bytes g4, label bytes l4
+template <int C>
+__device__ __forceinline__ void count_word(u64& lo, u64& hi, unsigned int g4, unsigned int l4) {
+  const unsigned int g0 = g4 & 0xffu, l0 = l4 & 0xffu;
+  if (g4 == g0 * 0x01010101u && l4 == l0 * 0x01010101u) {  // masks are piecewise constant: the common case
+    if (g0 < (unsigned)C) count_bin(lo, hi, g0 * C + l0, 4u);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned int gg = (g4 >> (8 * j)) & 0xffu;
+      if (gg < (unsigned)C) count_bin(lo, hi, gg * C + ((l4 >> (8 * j)) & 0xffu), 1u);
+    }
+  }
+}
 
 // ---- the row loop of one strip, K difference fields ----------------------------------------------------------------
-template <int C, int G, int F, int NP, int K>
+// LSM: labels go to the shared-memory label tile (background / confusion / the global store happen in the vector pass
+// after the exact pass); otherwise they go straight to global memory with the byte masks prefetched 4 rows ahead.
+template <int C, int G, int F, int NP, int K, bool LSM>
 __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeom& g, FCtl* ctl, uint32_t* queue, int b,
                                             uint32_t rowtab_s, uint32_t rowoff_s, uint32_t colA_t, uint32_t colB_t, uint32_t ymap_s,
-                                            int n, int x, int ys, int ye, const int (&cls)[C], float tau, u64& cnt_lo, u64& cnt_hi) {
+                                            uint32_t lab_s, int n, int x, int ys, int ye, const int (&cls)[C], float tau,
+                                            u64& cnt_lo, u64& cnt_hi) {
   constexpr bool RT = F < 0;
   constexpr int RS = 16 * ((G + 2) / 2);
   const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
@@ -111,6 +217,9 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   const bool has_label = RT ? (p.label_out != nullptr) : ((F & 16) != 0);
   const int T_w = p.T_w;
   const uint32_t colg = 16u * g.GXP;
+  unsigned int c4[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) c4[k] = 0x01010101u * (unsigned)cls[k < C ? k : 0];
 
   u64 Hb[G][K][NP], Dh[G][K][NP], base[K][NP];
   // horizontally interpolated values of one row (byte offset `row` inside a map) of every difference map of group gi
@@ -152,48 +261,60 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   }
   rebase();
 
-  const long long pix0 = ((long long)n * p.T_h + ys) * T_w + x;
-  const uint8_t* bgp = has_bg ? p.bg + pix0 : nullptr;
-  const uint8_t* gtp = do_conf ? p.gt + pix0 : nullptr;
-  uint8_t* lbp = has_label ? p.label_out + pix0 : nullptr;
   uint32_t rt = rowtab_s + RS * ys, ro_a = rowoff_s + 8u * G * ys;
-  // byte masks are fetched two rows ahead of their use
-  unsigned int bg_c = 0, bg_n = 0, gt_c = 0, gt_n = 0;
-  if (has_bg) {
-    bg_c = ldg_px<NP>(bgp);
-    if (ys + 1 < ye) bg_n = ldg_px<NP>(bgp + T_w);
-    bgp += 2 * T_w;
-  }
-  if (do_conf) {
-    gt_c = ldg_px<NP>(gtp);
-    if (ys + 1 < ye) gt_n = ldg_px<NP>(gtp + T_w);
-    gtp += 2 * T_w;
+  uint32_t lab_a = lab_s + ys * T_w + x;
+  // direct mode: byte masks are fetched 4 rows ahead of their use (rows past the strip are clamped, never out of bounds)
+  constexpr int PD = 4;
+  const long long tbase = (long long)n * p.T_h * T_w + x;
+  const uint8_t* bgt = (!LSM && has_bg) ? p.bg + tbase : nullptr;
+  const uint8_t* gtt = (!LSM && do_conf) ? p.gt + tbase : nullptr;
+  uint8_t* lbp = (!LSM && has_label) ? p.label_out + tbase + (long long)ys * T_w : nullptr;
+  unsigned int bgq[PD], gtq[PD];
+#pragma unroll
+  for (int j = 0; j < PD; j++) {
+    bgq[j] = 0; gtq[j] = 0;
+    if (!LSM) {
+      const int r = min(ys + j, ye - 1) * T_w;
+      if (has_bg) bgq[j] = ldg_px<NP>(bgt + r);
+      if (do_conf) gtq[j] = ldg_px<NP>(gtt + r);
+    }
   }
   const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match, bgl4 = 0x01010101u * (unsigned)p.bg_label;
 
+  // the row-table entry (vertical weights + "source rows moved" flags) is fetched one row ahead of its use
+  auto load_rowtab = [&](uint32_t a, u64 (&w)[G], unsigned int& flags) {
+    const ulonglong2 t0 = lds_u64x2(a);
+    if (G == 1) { w[0] = t0.x; flags = (unsigned int)t0.y; }
+    else {
+      w[0] = t0.x; w[G > 1 ? 1 : 0] = t0.y;
+      const ulonglong2 t1 = lds_u64x2(a + 16u);
+      if (G == 2) flags = (unsigned int)t1.x;
+      else {
+        w[G > 2 ? 2 : 0] = t1.x;
+        if (G == 3) flags = (unsigned int)t1.y;
+        else { const ulonglong2 t2 = lds_u64x2(a + 32u); w[G - 1] = t2.x; flags = (unsigned int)t2.y; }
+      }
+    }
+  };
+  u64 wn[G];
+  unsigned int flagsn;
+  load_rowtab(rt, wn, flagsn);
 #pragma unroll 1
   for (int yl = ys; yl < ye; yl++) {
     u64 w[G];
-    unsigned int flags;
-    {
-      const ulonglong2 t0 = lds_u64x2(rt);
-      if (G == 1) { w[0] = t0.x; flags = (unsigned int)t0.y; }
-      else {
-        w[0] = t0.x; w[1] = t0.y;
-        const ulonglong2 t1 = lds_u64x2(rt + 16u);
-        if (G == 2) flags = (unsigned int)t1.x;
-        else {
-          w[2] = t1.x;
-          if (G == 3) flags = (unsigned int)t1.y;
-          else { const ulonglong2 t2 = lds_u64x2(rt + 32u); w[G - 1] = t2.x; flags = (unsigned int)t2.y; }
-        }
-      }
-    }
-    const unsigned int bg4 = bg_c, gt4 = gt_c;
-    bg_c = bg_n; gt_c = gt_n;
-    if (yl + 2 < ye) {
-      if (has_bg) { bg_n = ldg_px<NP>(bgp); bgp += T_w; }
-      if (do_conf) { gt_n = ldg_px<NP>(gtp); gtp += T_w; }
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) w[gi] = wn[gi];
+    const unsigned int flags = flagsn;
+    rt += RS;
+    load_rowtab(rt, wn, flagsn);  // (one entry past the strip is read and discarded; it stays inside the shared-memory tables)
+    unsigned int bg4 = 0, gt4 = 0;
+    if (!LSM) {
+      bg4 = bgq[0]; gt4 = gtq[0];
+#pragma unroll
+      for (int j = 0; j + 1 < PD; j++) { bgq[j] = bgq[j + 1]; gtq[j] = gtq[j + 1]; }
+      const int r = min(yl + PD, ye - 1) * T_w;
+      if (has_bg) bgq[PD - 1] = ldg_px<NP>(bgt + r);
+      if (do_conf) gtq[PD - 1] = ldg_px<NP>(gtt + r);
     }
     if (flags) {  // the bracketing source rows of at least one group moved down by one
 #pragma unroll
@@ -210,51 +331,121 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
       }
       rebase();
     }
-    rt += RS; ro_a += 8u * G;
+    ro_a += 8u * G;
 
-    unsigned int lab4 = 0, unc = 0;
-    int labs[2 * NP];
+    u64 acc[K][NP];
 #pragma unroll
-    for (int q = 0; q < NP; q++) {
-      float d0[K], d1[K];
+    for (int k = 0; k < K; k++)
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        u64 acc = base[k][q];
+      for (int q = 0; q < NP; q++) {
+        u64 a = base[k][q];
 #pragma unroll
-        for (int gi = 0; gi < G; gi++) acc = fma2(w[gi], Dh[gi][k][q], acc);
-        unpack2(acc, d0[k], d1[k]);
+        for (int gi = 0; gi < G; gi++) a = fma2(w[gi], Dh[gi][k][q], a);
+        acc[k][q] = a;
       }
-      const bool c0 = decide_diff<K, C>(d0, cls, tau, labs[2 * q]);
-      const bool c1 = decide_diff<K, C>(d1, cls, tau, labs[2 * q + 1]);
-      unc |= (c0 ? 0u : 1u) << (2 * q);
-      unc |= (c1 ? 0u : 1u) << (2 * q + 1);
-      lab4 |= ((unsigned)labs[2 * q] | ((unsigned)labs[2 * q + 1] << 8)) << (16 * q);
+    unsigned int lab4, unc = 0;
+    if (!labels_from_diffs<K, NP>(acc, c4, tau, lab4)) {
+      unc = uncertain_mask<K, NP, C>(acc, cls, tau);
+      if (unc) push_uncertain(ctl, queue, b, yl, x, unc);
     }
-    if (unc) push_uncertain(ctl, queue, b, yl, x, unc);
-    if (do_conf) {
+    if (LSM) {
+      sts_px<NP>(lab_a, lab4);
+      lab_a += T_w;
+    } else {
+      if (do_conf) {
+        if (NP == 2 && unc == 0) count_word<C>(cnt_lo, cnt_hi, gt4, lab4);
+        else {
 #pragma unroll
-      for (int j = 0; j < 2 * NP; j++) {
-        const unsigned int gg = (gt4 >> (8 * j)) & 0xffu;
-        if (gg < (unsigned)C && !((unc >> j) & 1u)) {
-          const unsigned int bn = gg * C + labs[j];
-          const u64 inc = 1ull << (8 * (bn & 7));
-          if (bn < 8) cnt_lo += inc; else cnt_hi += inc;
+          for (int j = 0; j < 2 * NP; j++) {
+            const unsigned int gg = (gt4 >> (8 * j)) & 0xffu;
+            if (gg < (unsigned)C && !((unc >> j) & 1u)) count_bin(cnt_lo, cnt_hi, gg * C + ((lab4 >> (8 * j)) & 0xffu), 1u);
+          }
         }
       }
-    }
-    if (has_label) {
-      unsigned int o = lab4;
-      if (has_bg) {
-        const unsigned int eq = __vcmpeq4(bg4, m4);
-        o = (bgl4 & eq) | (lab4 & ~eq);
+      if (has_label) {
+        unsigned int o = lab4;
+        if (has_bg) {
+          const unsigned int eq = __vcmpeq4(bg4, m4);
+          o = (bgl4 & eq) | (lab4 & ~eq);
+        }
+        stg_px<NP>(lbp, o);
+        lbp += T_w;
       }
-      stg_px<NP>(lbp, o);
-      lbp += T_w;
     }
   }
 }
 
-template <int C, int V, int G, int F, int NP>
+// ---- pre-pass: Y[g][k] = sum over the views of group g of (x[c_{k+1}] - x[c_0]) at low resolution, in the de-augmented
+// frame; returns the thread's max |x| (NaN-propagating).  When every group is a (view 2g, view 2g+1) pair -- a scale and its
+// flipped twin, the BASELINE layout -- both views are read in one sweep; otherwise the first view of a group writes and the
+// others add (a thread always revisits its own cells, so the read-modify-write needs no synchronisation).
+template <int C, int V, int G, int K>
+__device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint32_t (&vb)[V], const int (&cls)[C], uint32_t ymap_s, int tid, int nt) {
+  float mxf = 0.f;
+  if constexpr (V == 2 * G) {
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+      constexpr int dummy = 0; (void)dummy;
+      const int va = 2 * gi < V ? 2 * gi : 0, vc = 2 * gi + 1 < V ? 2 * gi + 1 : 0;
+      const int wo = g.g_wo[gi], cells = g.g_ho[gi] * wo;
+      const unsigned int inv = g.g_inv[gi];
+      const uint32_t ym = ymap_s + g.g_ybytes[gi];
+      const int ra = g.vrow[va], ca = g.vcol[va], rb = g.vrow[vc], cb = g.vcol[vc];
+      const uint32_t basea = vb[va] + g.vbase[va] + cls[0] * g.plane_bytes[va];
+      const uint32_t baseb = vb[vc] + g.vbase[vc] + cls[0] * g.plane_bytes[vc];
+      int dqa[K], dqb[K];
+#pragma unroll
+      for (int q = 0; q < K; q++) { dqa[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[va]; dqb[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[vc]; }
+#pragma unroll 2
+      for (int idx = tid; idx < cells; idx += nt) {
+        const int i = (int)__umulhi((unsigned)idx, inv), j = idx - i * wo;
+        const uint32_t aa = basea + i * ra + j * ca, ab = baseb + i * rb + j * cb;
+        const float x0a = lds_f32(aa), x0b = lds_f32(ab);
+        mxf = max_nan(max_nan(mxf, fabsf(x0a)), fabsf(x0b));
+        uint32_t ya = ym + 4u * idx;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+          const float xa = lds_f32(aa + dqa[q]), xb = lds_f32(ab + dqb[q]);
+          mxf = max_nan(max_nan(mxf, fabsf(xa)), fabsf(xb));
+          sts_f32(ya, __fadd_rn(__fsub_rn(xa, x0a), __fsub_rn(xb, x0b)));
+          ya += 4u * cells;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const int gi = g.group_of[v];
+      const bool first = g.first_in_group[v] != 0;
+      const int wo = g.g_wo[gi], cells = g.g_ho[gi] * wo, vrow = g.vrow[v], vcol = g.vcol[v];
+      const unsigned int inv = g.g_inv[gi];
+      const uint32_t ym = ymap_s + g.g_ybytes[gi];
+      const uint32_t base0 = vb[v] + g.vbase[v] + cls[0] * g.plane_bytes[v];
+      int dq[K];
+#pragma unroll
+      for (int q = 0; q < K; q++) dq[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[v];
+      for (int idx = tid; idx < cells; idx += nt) {
+        const int i = (int)__umulhi((unsigned)idx, inv), j = idx - i * wo;
+        const uint32_t a = base0 + i * vrow + j * vcol;
+        const float x0 = lds_f32(a);
+        mxf = max_nan(mxf, fabsf(x0));
+        uint32_t ya = ym + 4u * idx;
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+          const float xq = lds_f32(a + dq[q]);
+          mxf = max_nan(mxf, fabsf(xq));
+          float t = __fsub_rn(xq, x0);
+          if (!first) t = __fadd_rn(lds_f32(ya), t);
+          sts_f32(ya, t);
+          ya += 4u * cells;
+        }
+      }
+    }
+  }
+  return mxf;
+}
+
+template <int C, int V, int G, int F, int NP, bool LSM>
 __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __grid_constant__ FuseParams p,
                                                                       const __grid_constant__ FilterGeom g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -266,6 +457,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   float4* lowcol = reinterpret_cast<float4*>(smem_raw + g.lowcol_off);    // [low_w][V]
   float* ymap = reinterpret_cast<float*>(smem_raw + g.ymap_off);          // [G][C-1][ho][wo] difference maps
   uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + g.queue_off);  // [kFQueueCap] (y << 16) | x
+  uint8_t* labsm = smem_raw + (LSM ? g.lab_off : 0);                      // [T_h][T_w] labels of the current tile (LSM)
   float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);          // 2 staging buffers
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -282,11 +474,12 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   if (tid == 0) {
     mbar_init(&ctl->full[0], 1);
     mbar_init(&ctl->full[1], 1);
-    mbar_init(&ctl->empty[0], g.cwarps);
-    mbar_init(&ctl->empty[1], g.cwarps);
+    mbar_init(&ctl->empty[0], g.cwarps + (need_low ? kFAux : 0));
+    mbar_init(&ctl->empty[1], g.cwarps + (need_low ? kFAux : 0));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     ctl->maxbits[0] = ctl->maxbits[1] = 0u;
     ctl->qcount[0] = ctl->qcount[1] = 0u;
+    ctl->lownext[0] = ctl->lownext[1] = 0u;
   }
   for (int i = tid; i < 64; i += nthreads) ctl->hist[i] = 0;
   for (int y = tid; y < T_h; y += nthreads) {
@@ -360,26 +553,92 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 
   __syncthreads();  // barriers + tables visible to every warp
 
-  const int ncomp = g.cwarps * 32;  // compute threads; the last warp of the CTA is the producer
-  if (tid >= ncomp) {
+  const int ncomp = g.cwarps * 32;  // compute threads, then kFAux export warps; the last warp of the CTA is the producer
+  if (tid >= ncomp + 32 * kFAux) {
     // ===== producer warp: claims tiles, publishes their ids, fetches their views (TMA) one tile ahead of the compute warps
-    if (tid == ncomp) {
+    if (tid == ncomp + 32 * kFAux) {
       const long long tile_px = (long long)T_h * T_w;
+      // the tile id (global atomic) and its presence vector are fetched one step ahead, so that only the TMA itself sits
+      // between a staging buffer becoming free and its refill
+      int next = atomicAdd(g.counter, 1);
+      bool next_views = next < p.N && tile_needs_views(next);
       for (int k = 0;; k++) {
         const int b = k & 1;
-        if (k >= 2) mbar_wait(&ctl->empty[b], ((k >> 1) - 1) & 1);  // all compute warps are done with buffer b
-        const int t = atomicAdd(g.counter, 1);
-        const int tile = t < p.N ? t : -1;
+        if (k >= 2) mbar_wait_sleep(&ctl->empty[b], ((k >> 1) - 1) & 1);  // every warp is done with buffer b
+        const int tile = next < p.N ? next : -1;
         ctl->tile[b] = tile;
-        if (tile >= 0 && tile_needs_views(tile)) issue_tile(tile, b);
+        ctl->lownext[b] = 0u;
+        if (tile >= 0 && next_views) issue_tile(tile, b);
         else mbar_arrive(&ctl->full[b]);
         if (tile < 0) break;
-        // pull the tile's byte masks into L2 ahead of the per-row loads
+        // pull the tile's byte masks into L2 ahead of their use
         if (tile_px % 16 == 0) {
           if (has_bg && ((uintptr_t)p.bg & 15) == 0) bulk_prefetch_l2(p.bg + tile * tile_px, (uint32_t)tile_px);
           if (do_conf && ((uintptr_t)p.gt & 15) == 0) bulk_prefetch_l2(p.gt + tile * tile_px, (uint32_t)tile_px);
         }
+        next = atomicAdd(g.counter, 1);
+        next_views = next < p.N && tile_needs_views(next);
       }
+    }
+    return;
+  }
+
+  // ---- the 32x32 logits of tile n (infer_pseudo_masks.py:126), exact and in the reference's operation order.  Low-resolution
+  // rows are claimed one at a time from a shared counter by whichever warp has nothing better to do: the export warps all the
+  // time, the compute warps once their own work on the tile is finished.  Lane = low-resolution column; per (view, class) the
+  // two bracketing source rows are interpolated horizontally once (Ta, Tb) and blended vertically.
+  auto export_rows = [&](int n, int b, const uint32_t (&vb)[V]) {
+    const int lane = tid & 31;
+    const long long lplane = (long long)p.low_h * p.low_w;
+    for (;;) {
+      int ly = 0;
+      if (lane == 0) ly = (int)atomicAdd(&ctl->lownext[b], 1u);
+      ly = __shfl_sync(0xffffffffu, ly, 0);
+      if (ly >= p.low_h) break;
+      for (int lxb = 0; lxb < p.low_w; lxb += 32) {
+        const int lx = min(lxb + lane, p.low_w - 1);
+        float a[C];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const float4 R = lowrow[ly * V + v], Q = lowcol[lx * V + v];
+          const uint32_t r0 = vb[v] + __float_as_int(R.z), r1 = vb[v] + __float_as_int(R.w);
+          const uint32_t c0 = __float_as_int(Q.z), c1 = __float_as_int(Q.w);
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const uint32_t pl = c * g.plane_bytes[v];
+            const float ta = __fmaf_rn(Q.x, lds_f32(r0 + pl + c0), __fmul_rn(Q.y, lds_f32(r0 + pl + c1)));
+            const float tb = __fmaf_rn(Q.x, lds_f32(r1 + pl + c0), __fmul_rn(Q.y, lds_f32(r1 + pl + c1)));
+            const float u = __fmaf_rn(R.x, ta, __fmul_rn(R.y, tb));
+            a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+          }
+        }
+        if (lxb + lane < p.low_w) {
+          float* outp = p.lowres_out + (long long)n * C * lplane + (long long)ly * p.low_w + lxb + lane;
+#pragma unroll
+          for (int c = 0; c < C; c++) outp[c * lplane] = pisto_div_views(a[c], p.dec);
+        }
+      }
+    }
+  };
+
+  if (tid >= ncomp) {
+    // ===== export warps
+    if (!need_low) return;
+    for (int k = 0;; k++) {
+      const int b = k & 1;
+      mbar_wait(&ctl->full[b], (k >> 1) & 1);
+      const int n = ctl->tile[b];
+      if (n < 0) break;
+      uint32_t vb[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const ViewDev& vw = p.view[v];
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+        vb[v] = smem_u32(vsm + b * g.buf_floats + g.view_off[v]) + sh;
+      }
+      export_rows(n, b, vb);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&ctl->empty[b]);
     }
     return;
   }
@@ -392,8 +651,9 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   const int ye = g.strip_y0[strip + 1];
   const uint32_t rowtab_s = smem_u32(smem_raw + g.rowtab_off), rowoff_s = smem_u32(rowoff), ymap_s = smem_u32(ymap);
   const uint32_t colA_t = smem_u32(colA) + 16u * NP * grp, colB_t = smem_u32(colB) + 16u * NP * grp;
+  const uint32_t lab_s = smem_u32(labsm);
   const int nt = ncomp;  // cooperative loops below run over the compute threads only
-  const int npt = need_low ? p.low_h * p.low_w : 0;
+  const long long tpx = (long long)T_h * T_w;
 
   for (int k = 0;; k++) {
     const int b = k & 1;
@@ -427,43 +687,15 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 
     // ---- pre-pass: low-resolution difference maps of every scale group + max |x| ------------------------------------
     if (multi && P >= 2) {
-      unsigned int mx = 0;
-#pragma unroll 1
-      for (int gi = 0; gi < G; gi++) {
-        const int wo = g.g_wo[gi], cells = g.g_ho[gi] * wo;
-        float* ym = ymap + (g.g_ybytes[gi] >> 2);
-        for (int idx = tid; idx < cells; idx += nt) {
-          const int i = idx / wo, j = idx - i * wo;
-          float y[C - 1];
-#pragma unroll
-          for (int q = 0; q < C - 1; q++) y[q] = 0.f;
-          bool first = true;
-#pragma unroll
-          for (int v = 0; v < V; v++) {
-            if (g.group_of[v] != gi) continue;
-            const uint32_t a = vb[v] + g.vbase[v] + i * g.vrow[v] + j * g.vcol[v];
-            const float x0 = lds_f32(a + cls[0] * g.plane_bytes[v]);
-            mx = max(mx, __float_as_uint(x0) & 0x7fffffffu);
-#pragma unroll
-            for (int q = 0; q < C - 1; q++) {
-              if (q + 1 < P) {
-                const float xq = lds_f32(a + cls[q + 1] * g.plane_bytes[v]);
-                mx = max(mx, __float_as_uint(xq) & 0x7fffffffu);
-                const float t = __fsub_rn(xq, x0);
-                y[q] = first ? t : __fadd_rn(y[q], t);
-              }
-            }
-            first = false;
-          }
-#pragma unroll
-          for (int q = 0; q < C - 1; q++)
-            if (q + 1 < P) ym[q * cells + idx] = y[q];
-        }
-      }
-      mx = __reduce_max_sync(0xffffffffu, mx);
+      float mxf;
+      if (P == 2) mxf = filter_prepass<C, V, G, 1>(g, vb, cls, ymap_s, tid, nt);
+      else if (P == 3) mxf = filter_prepass<C, V, G, 2>(g, vb, cls, ymap_s, tid, nt);
+      else mxf = filter_prepass<C, V, G, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));  // NaN (0x7fffffff) > Inf > finite
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
-    bar_sync(1, ncomp);  // difference maps + max visible
+    bar_sync(1, ncomp);  // difference maps + max visible; every thread has left the previous tile
+    if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone; its slot is next pushed to after the next bar_sync
 
     bool exact_all = false;
     if (multi) {
@@ -471,102 +703,26 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       if (P >= 2) {
         const float A = __fmul_rn((float)V, __uint_as_float(ctl->maxbits[b]));
         tau = __fmaf_rn(A, g.tau_coef, g.tau_abs);
-        if (!(A < 1e9f)) exact_all = true;  // non-finite or absurd magnitudes: follow the reference everywhere
+        if (!(A < 5e8f)) exact_all = true;  // non-finite or absurd magnitudes: follow the reference everywhere
       } else {
-        exact_all = true;                   // empty presence vector
+        exact_all = true;                   // empty (or one-class NEG_INF) presence vector
       }
       if (!exact_all && worker && ys < ye) {
-        if (P == 2) filter_rows<C, G, F, NP, 1>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-        else if (P == 3) filter_rows<C, G, F, NP, 2>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-        else if (C >= 4 && P == 4) filter_rows<C, G, F, NP, (C >= 4 ? 3 : 1)>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        if (P == 2) filter_rows<C, G, F, NP, 1, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        else if (P == 3) filter_rows<C, G, F, NP, 2, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        else if (C >= 4 && P == 4) filter_rows<C, G, F, NP, (C >= 4 ? 3 : 1), LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
       }
-    } else {
-      // single-label tile (infer_pseudo_masks.py:71-73): constant label + background overwrite, 16 pixels per thread-step
-      const long long tpx = (long long)T_h * T_w;
-      const long long base = (long long)n * tpx;
-      const unsigned int lab4 = 0x01010101u * (unsigned)tp.single, bgl4 = 0x01010101u * (unsigned)p.bg_label;
-      // packed 8-bit confusion counters: at most 255 pixels per thread between flushes
-      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0) &&
-                          (!do_conf || 16 * ((tpx / 16 + nt - 1) / nt) <= 255);
-      const long long nvec = vec_ok ? tpx / 16 : 0;
-      const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
-      auto sel4 = [&](unsigned int w) -> unsigned int {
-        const unsigned int eq = __vcmpeq4(w, m4);  // 0xff in every byte equal to bg_match
-        return (bgl4 & eq) | (lab4 & ~eq);
-      };
-      constexpr int UN = 4;  // independent 16-byte loads in flight per thread
-      for (long long i0 = tid; i0 < nvec; i0 += (long long)UN * nt) {
-        uint4 bgv[UN], gv[UN];
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const long long i = i0 + (long long)u * nt;
-          if (i < nvec) {
-            if (has_bg) bgv[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
-            if (do_conf) gv[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const long long i = i0 + (long long)u * nt;
-          if (i < nvec) {
-            uint4 o = make_uint4(lab4, lab4, lab4, lab4);
-            if (has_bg) o = make_uint4(sel4(bgv[u].x), sel4(bgv[u].y), sel4(bgv[u].z), sel4(bgv[u].w));
-            if (do_conf) {
-              const unsigned int gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-#pragma unroll
-              for (int q = 0; q < 4; q++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                  const unsigned int gg = (gw[q] >> (8 * j)) & 0xffu;
-                  if (gg < (unsigned)C) { const unsigned int bn = gg * C + tp.single; const u64 inc = 1ull << (8 * (bn & 7)); if (bn < 8) cnt_lo += inc; else cnt_hi += inc; }
-                }
-            }
-            if (has_label) reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
-          }
-        }
-      }
-      for (long long i = nvec * 16 + tid; i < tpx; i += nt) {  // unaligned / ragged remainder
-        unsigned int o = (unsigned)tp.single;
-        if (has_bg && p.bg[base + i] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
-        if (do_conf) {
-          const unsigned int gg = p.gt[base + i];
-          if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + tp.single], 1u);
-        }
-        if (has_label) p.label_out[base + i] = (uint8_t)o;
-      }
+      bar_sync(1, ncomp);  // every strip done: the queue is complete
+      if (tid == 0) ctl->maxbits[b] = 0u;  // read by everyone before this barrier; next written two tiles from now
     }
-    bar_sync(1, ncomp);  // every strip done: the queue is complete
-    if (tid == 0) { ctl->maxbits[b] = 0u; ctl->qcount[b ^ 1] = 0u; }
 
-    // ---- exact pass: 32x32 gather points (always) + queued pixels (or the whole tile) --------------------------------
-    int nfix = 0;
+    // ---- exact pass: queued pixels (or the whole tile), operation by operation as the reference ----------------------
     if (multi) {
       const unsigned int nq = ctl->qcount[b];
-      if (nq > (unsigned)kFQueueCap && !exact_all) { exact_all = true; cnt_lo = cnt_hi = 0; }  // overflow: recount the whole tile
-      nfix = exact_all ? T_h * T_w : (int)nq;
-    }
-    for (int it = tid; it < npt + nfix; it += nt) {
-      float a[C];
-      if (it < npt) {
-        const int ly = it / p.low_w, lx = it - ly * p.low_w;
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const float4 R = lowrow[ly * V + v], Q = lowcol[lx * V + v];
-          const uint32_t r0 = vb[v] + __float_as_int(R.z), r1 = vb[v] + __float_as_int(R.w);
-          const uint32_t c0 = __float_as_int(Q.z), c1 = __float_as_int(Q.w);
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            const uint32_t pl = c * g.plane_bytes[v];
-            const float h0 = __fmaf_rn(Q.x, lds_f32(r0 + pl + c0), __fmul_rn(Q.y, lds_f32(r0 + pl + c1)));
-            const float h1 = __fmaf_rn(Q.x, lds_f32(r1 + pl + c0), __fmul_rn(Q.y, lds_f32(r1 + pl + c1)));
-            const float u = __fmaf_rn(R.x, h0, __fmul_rn(R.y, h1));
-            a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < C; c++) p.lowres_out[((long long)n * C + c) * npt + it] = pisto_div_views(a[c], p.dec);
-      } else {
-        const int j = it - npt;
+      if (nq > (unsigned)kFQueueCap && !exact_all) { exact_all = true; cnt_lo = cnt_hi = 0; }  // overflow: redo the whole tile
+      const int nfix = exact_all ? T_h * T_w : (int)nq;
+      for (int j = tid; j < nfix; j += nt) {
+        float a[C];
         int yy, xx;
         if (exact_all) { yy = j / T_w; xx = j - yy * T_w; }
         else { const uint32_t e = queue[j]; yy = (int)(e >> 16); xx = (int)(e & 0xffffu); }
@@ -587,18 +743,82 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
           }
         }
         const int lab = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
-        const long long pix = ((long long)n * T_h + yy) * T_w + xx;
-        if (do_conf) {
-          const unsigned int gg = p.gt[pix];
-          if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
-        }
-        if (has_label) {
-          unsigned int o = (unsigned)lab;
-          if (has_bg && p.bg[pix] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
-          p.label_out[pix] = (uint8_t)o;
+        if (LSM) {
+          labsm[yy * T_w + xx] = (uint8_t)lab;
+        } else {
+          const long long pix = (long long)n * tpx + yy * T_w + xx;
+          if (do_conf) {
+            const unsigned int gg = p.gt[pix];
+            if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
+          }
+          if (has_label) {
+            unsigned int o = (unsigned)lab;
+            if (has_bg && p.bg[pix] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+            p.label_out[pix] = (uint8_t)o;
+          }
         }
       }
     }
+    if (LSM && multi) bar_sync(1, ncomp);  // label tile complete
+
+    // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label) -----
+    if (LSM || !multi) {
+      const long long base = (long long)n * tpx;
+      const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
+      // packed 8-bit confusion counters: at most 255 pixels per thread between flushes
+      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0) &&
+                          (!do_conf || 16 * ((tpx / 16 + nt - 1) / nt) <= 255);
+      const int nvec = vec_ok ? (int)(tpx / 16) : 0;
+      const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
+      constexpr int UN = 4;  // independent 16-byte loads in flight per thread
+      for (int i0 = tid; i0 < nvec; i0 += UN * nt) {
+        uint4 bgv[UN], gv[UN], lv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          if (i < nvec) {
+            if (has_bg) bgv[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+            if (do_conf) gv[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+            if (LSM && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
+            else lv[u] = make_uint4(labc, labc, labc, labc);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          if (i < nvec) {
+            const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+            if (do_conf) {
+              const unsigned int gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+              for (int q = 0; q < 4; q++) count_word<C>(cnt_lo, cnt_hi, gw[q], lw[q]);
+            }
+            if (has_label) {
+              uint4 o = lv[u];
+              if (has_bg) {
+                const unsigned int bw[4] = {bgv[u].x, bgv[u].y, bgv[u].z, bgv[u].w};
+                unsigned int ow[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
+                o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+              reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
+            }
+          }
+        }
+      }
+      for (int i = nvec * 16 + tid; i < (int)tpx; i += nt) {  // unaligned / ragged shapes
+        const unsigned int lab = (LSM && multi) ? labsm[i] : (unsigned)tp.single;
+        unsigned int o = lab;
+        if (has_bg && p.bg[base + i] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+        if (do_conf) {
+          const unsigned int gg = p.gt[base + i];
+          if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
+        }
+        if (has_label) p.label_out[base + i] = (uint8_t)o;
+      }
+    }
+    if (need_low) export_rows(n, b, vb);  // whatever the export warps have not got to yet
     if (do_conf) {
       // every lane of every compute warp reaches this point: full-mask warp reductions are safe
 #pragma unroll
@@ -621,12 +841,12 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, FilterGeom* g) {
+static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, FilterGeom* g) {
   memset(g, 0, sizeof(*g));
   if (p.T_w % (2 * NP)) return false;
   const int GX = p.T_w / (2 * NP);
-  if (GX > kFMaxThreads - 32) return false;  // one warp of the CTA is the producer
-  int S = (kFMaxThreads - 32) / GX;
+  if (GX > kFMaxThreads - 32 - 32 * kFAux) return false;  // one producer warp, kFAux export warps
+  int S = (kFMaxThreads - 32 - 32 * kFAux) / GX;
   if (S > p.T_h) S = p.T_h;
   if (S > 32) S = 32;
   // scale groups: views with the same de-augmented size share their interpolation weights
@@ -634,6 +854,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
     if (vw.map.ho >= p.T_h) return false;  // same-size / down-sampling rows: the source-row pair does not move by exactly one
+    if (vw.map.ho * vw.map.wo >= 65536) return false;
     int gi = -1;
     for (int q = 0; q < G; q++)
       if (g->g_ho[q] == vw.map.ho && g->g_wo[q] == vw.map.wo) gi = q;
@@ -642,8 +863,10 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
       gi = G++;
       g->g_ho[gi] = vw.map.ho; g->g_wo[gi] = vw.map.wo; g->g_same_w[gi] = vw.same_w;
       g->g_scale_h[gi] = vw.scale_h; g->g_scale_w[gi] = vw.scale_w;
+      g->g_inv[gi] = (unsigned int)(((1ull << 32) + vw.map.wo - 1) / vw.map.wo);
     }
     g->group_of[v] = gi;
+    g->first_in_group[v] = cnt[gi] == 0;
     if (++cnt[gi] > nmax) nmax = cnt[gi];
     g->plane_bytes[v] = 4 * vw.h * vw.w;
     g->vbase[v] = 4 * (vw.map.a0 * vw.w + vw.map.b0);
@@ -651,6 +874,9 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
     g->vcol[v] = 4 * (vw.map.aj * vw.w + vw.map.bj);
   }
   if (G != G_expected) return false;
+  if (p.V == 2 * G)  // the paired pre-pass assumes views (2g, 2g+1) form group g
+    for (int v = 0; v < p.V; v++)
+      if (g->group_of[v] != v / 2) return false;
   // strips: when the flag pattern of the row table repeats with a period that divides T_h / S, every strip starts at
   // the same phase and the lanes of a warp that straddles two strips refill together
   int period = 1;
@@ -663,7 +889,6 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
     period = period / x * pv;
   }
   if (period > 1 && p.T_h % period == 0) {
-    // prefer a strip count whose strips are whole periods and that fills the CTA best
     int best = 0;
     for (int s = 1; s <= S; s++)
       if ((p.T_h / period) % s == 0) best = s;
@@ -671,11 +896,11 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   }
   g->GX = GX; g->S = S; g->GXP = p.T_w / 2;
   g->cwarps = (GX * S + 31) / 32;
-  g->threads = g->cwarps * 32 + 32;
+  g->threads = g->cwarps * 32 + 32 * kFAux + 32;
   int rps = 0;
   for (int q = 0; q <= S; q++) g->strip_y0[q] = (int)((long long)p.T_h * q / S);
   for (int q = 0; q < S; q++) rps = max(rps, g->strip_y0[q + 1] - g->strip_y0[q]);
-  if (rps * 2 * NP > 255) return false;  // packed 8-bit confusion counters
+  if (rps * 2 * NP > 255) return false;  // packed 8-bit confusion counters (direct mode)
   int fl = 0;
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
@@ -683,20 +908,21 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
     fl += (p.C * vw.h * vw.w + 3 /* alignment shift */ + 3 /* tail */ + 3) & ~3;
   }
   g->buf_floats = fl;
-  // decision threshold: both evaluations differ from the exact difference of the view sums by at most
-  // cE * 2^-24 * A each way; on top of that the lead must cover the softmax margin 2.4e-7 * |a| + V * 2e-6 of common.cuh
-  const float cE = 2.f * nmax + 4.f * G + 2.f * p.V + 16.f;
+  // decision threshold: the interpolated differences and the exact view sums each differ from the real-number
+  // value by at most cE/2-ish * 2^-24 * A; on top of that the lead must cover the softmax margin 2.4e-7 * |a| + V * 2e-6 of common.cuh
+  const float cE = 2.f * nmax + 4.f * G + 2.f * p.V + 20.f;
   g->tau_coef = 2.f * cE * 5.9604645e-8f + 2.5e-7f;
   g->tau_abs = p.dec.margin_abs * 1.01f;
   const int RS = 16 * ((G + 2) / 2);
+  const bool low = p.lowres_out && p.low_fh > 0;
   int off = 0;
   g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
   g->rowtab_off = off; off += RS * p.T_h;
   g->rowoff_off = off; off += 8 * G * p.T_h; off = (off + 15) & ~15;
   g->cola_off = off; off += 16 * G * g->GXP;
   g->colb_off = off; off += 16 * G * g->GXP;
-  g->lowrow_off = off; off += 16 * p.V * (p.lowres_out && p.low_fh > 0 ? p.low_h : 0);
-  g->lowcol_off = off; off += 16 * p.V * (p.lowres_out && p.low_fh > 0 ? p.low_w : 0);
+  g->lowrow_off = off; off += 16 * p.V * (low ? p.low_h : 0);
+  g->lowcol_off = off; off += 16 * p.V * (low ? p.low_w : 0);
   g->ymap_off = off;
   for (int q = 0; q < G; q++) {
     g->g_ybytes[q] = off - g->ymap_off;
@@ -705,17 +931,19 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
     off = (off + 15) & ~15;
   }
   g->queue_off = off; off += 4 * kFQueueCap;
+  g->lab_off = off;
+  if (lsm) { off += p.T_h * p.T_w; off = (off + 15) & ~15; }
   off = (off + 127) & ~127;
   g->views_off = off; off += 2 * 4 * fl;
   g->smem_bytes = off;
   return off <= h->smem_optin - 1024;
 }
 
-template <int C, int V, int G, int F, int NP>
+template <int C, int V, int G, int F, int NP, bool LSM>
 int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   FilterGeom g;
-  if (!make_filter_geom(h, p, NP, G, &g)) return PISTO_OK;  // not launched: caller falls back
-  auto kern = fuse_filter_kernel<C, V, G, F, NP>;
+  if (!make_filter_geom(h, p, NP, G, LSM, &g)) return PISTO_OK;  // not launched: caller falls back
+  auto kern = fuse_filter_kernel<C, V, G, F, NP, LSM>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
@@ -747,12 +975,23 @@ static inline int pisto_filter_groups(const FuseParams& p) {
   return G;
 }
 
-template <int C, int V, int G, int NP>
-static int pisto_launch_filter_cvg(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+// labels staged in shared memory when the tile fits next to the staging buffers, else written directly
+template <int C, int V, int G, int F>
+static int pisto_launch_filter_f(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
+  if (np == 2) {
+    const int rc = launch_filter<C, V, G, F, 2, true>(h, p, st, launched);
+    if (rc != PISTO_OK || *launched) return rc;
+    return launch_filter<C, V, G, F, 2, false>(h, p, st, launched);
+  }
+  return launch_filter<C, V, G, -1, 1, false>(h, p, st, launched);
+}
+
+template <int C, int V, int G>
+static int pisto_launch_filter_cvg(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   switch (pisto_filter_flags(p)) {
-    case 25: return launch_filter<C, V, G, 25, NP>(h, p, st, launched);  // bg + labels + 32x32        (config 2)
-    case 19: return launch_filter<C, V, G, 19, NP>(h, p, st, launched);  // bg + gt/conf + labels      (config 1)
-    case 18: return launch_filter<C, V, G, 18, NP>(h, p, st, launched);  // gt/conf + labels           (config 3, mIoUMask.forward)
-    default: return launch_filter<C, V, G, -1, NP>(h, p, st, launched);
+    case 25: return pisto_launch_filter_f<C, V, G, 25>(h, p, st, np, launched);  // bg + labels + 32x32        (config 2)
+    case 19: return pisto_launch_filter_f<C, V, G, 19>(h, p, st, np, launched);  // bg + gt/conf + labels      (config 1)
+    case 18: return pisto_launch_filter_f<C, V, G, 18>(h, p, st, np, launched);  // gt/conf + labels           (config 3, mIoUMask.forward)
+    default: return pisto_launch_filter_f<C, V, G, -1>(h, p, st, np, launched);
   }
 }

@@ -2,5 +2,5 @@
 #include "fuse_filter.cuh"
 
 int pisto_launch_filter_c3_v6(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
-  return np == 2 ? pisto_launch_filter_cvg<3, 6, 3, 2>(h, p, st, launched) : pisto_launch_filter_cvg<3, 6, 3, 1>(h, p, st, launched);
+  return pisto_launch_filter_cvg<3, 6, 3>(h, p, st, np, launched);
 }

@@ -1,0 +1,6 @@
+// Instantiations of the filtered streaming fusion kernel for C = 4, V = 6 (3 scales x flip: BASELINE config 3).
+#include "fuse_filter.cuh"
+
+int pisto_launch_filter_c4_v6(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
+  return pisto_launch_filter_cvg<4, 6, 3>(h, p, st, np, launched);
+}

@@ -32,8 +32,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a lost TMA must surface as a launch failure, never as a hung GPU
 #pragma unroll 1
-  for (int it = 0; it < (1 << 26); it++)
+  for (int it = 0; it < (1 << 24); it++) {
     if (mbar_try_wait(bar, parity)) return;
+    if (it >= 8) __nanosleep(100);  // a long wait should not take issue slots from the warps that still have work
+  }
+  __trap();
+}
+// same, for a lone waiter that should not compete for issue slots with the warps doing the work
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+  for (int it = 0; it < (1 << 24); it++) {
+    if (mbar_try_wait(bar, parity)) return;
+    __nanosleep(1000);
+  }
   __trap();
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -55,6 +66,8 @@ __device__ __forceinline__ int2 lds_i2(uint32_t a) { int2 v; asm volatile("ld.sh
 __device__ __forceinline__ int4 lds_i4(uint32_t a) { int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ ulonglong2 lds_u64x2(uint32_t a) { ulonglong2 v; asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a)); return v; }
 
+// NaN-propagating maximum (FMNMX.NAN)
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 // named barrier over `count` threads (a multiple of 32): the compute warps of a CTA whose last warp is a TMA producer
