@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpistoseg_b200.so")
+# PISTOSEG_B200_LIB: alternative build of the same library (kernel A/B experiments, tools/ab.sh)
+LIB_PATH = os.environ.get("PISTOSEG_B200_LIB") or os.path.join(_HERE, "libpistoseg_b200.so")
 
 MAX_VIEWS = 16
 MAX_CLASSES = 8

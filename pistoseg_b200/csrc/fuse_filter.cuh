@@ -34,8 +34,14 @@
 
 namespace {
 
-constexpr int kFMaxThreads = 512;
-constexpr int kFAux = 2;  // warps that evaluate the 32x32 logit export concurrently with the row loop
+#ifndef PISTO_FTHREADS
+#define PISTO_FTHREADS 512
+#endif
+constexpr int kFMaxThreads = PISTO_FTHREADS;
+#ifndef PISTO_FAUX
+#define PISTO_FAUX 2
+#endif
+constexpr int kFAux = PISTO_FAUX;  // warps that evaluate the 32x32 logit export concurrently with the row loop
 constexpr int kFQueueCap = 1024;
 constexpr int kFMaxGroups = 4;
 
@@ -281,7 +287,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   }
   const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match, bgl4 = 0x01010101u * (unsigned)p.bg_label;
 
-  // the row-table entry (vertical weights + "source rows moved" flags) is fetched one row ahead of its use
+  // row-table entry: vertical weights (-l0, duplicated for the packed fma) + "source rows moved" flags
   auto load_rowtab = [&](uint32_t a, u64 (&w)[G], unsigned int& flags) {
     const ulonglong2 t0 = lds_u64x2(a);
     if (G == 1) { w[0] = t0.x; flags = (unsigned int)t0.y; }
@@ -296,17 +302,12 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
       }
     }
   };
-  u64 wn[G];
-  unsigned int flagsn;
-  load_rowtab(rt, wn, flagsn);
 #pragma unroll 1
   for (int yl = ys; yl < ye; yl++) {
     u64 w[G];
-#pragma unroll
-    for (int gi = 0; gi < G; gi++) w[gi] = wn[gi];
-    const unsigned int flags = flagsn;
+    unsigned int flags;
+    load_rowtab(rt, w, flags);
     rt += RS;
-    load_rowtab(rt, wn, flagsn);  // (one entry past the strip is read and discarded; it stays inside the shared-memory tables)
     unsigned int bg4 = 0, gt4 = 0;
     if (!LSM) {
       bg4 = bgq[0]; gt4 = gtq[0];
