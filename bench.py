@@ -250,7 +250,6 @@ def run_ours(args):
             traffic = tj["dram_bytes_per_launch"] * (N / tj["tiles_per_launch"])
     except Exception:
         pass
-    fp32_instr_per_tile = T * T * C * len(sizes) * 3  # mul + fma + add per (pixel, class, view): the exact-order lower bound
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -258,9 +257,10 @@ def run_ours(args):
                    "tiles_per_step_per_gpu": N, "views": sizes, "parallelism": f"tile-sharded x{world}, no data-path collective",
                    "l2": f"inputs+outputs {bpt * N / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_per_tile": bpt, "kernel": "fuse_stream_kernel<3,6,2>",
-                     "note": "kernel is FP32-issue-bound, not HBM-bound (DESIGN.md): fp32_frac = exact-order FP32 instr / (148 SM x 128 lanes x sm clock)",
-                     "fp32_frac": fp32_instr_per_tile * N / (per_launch_ms * 1e-3) / (148 * 128 * (clocks["sm_mhz"] if clocks else 1965.0) * 1e6)},
+                     "peak_source": peak_src, "bytes_per_tile": bpt, "kernel": "fuse_filter_kernel<C=3,V=6,G=3,F=25,NP=2,LSM=1>",
+                     "note": "achieved = algorithmic bytes/tile (SURVEY.md 8(d)) x tiles per launch / CUDA-event time per launch; traffic = ncu "
+                             "dram read+write bytes of one launch (profiles/traffic.json) scaled to this launch size; the kernel is "
+                             "issue/latency-bound, not DRAM-bound (DESIGN.md 4.1, profiles/)"},
         "e2e": {"value": world * Ne * args.e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "tiles_per_step_per_gpu": Ne, "api": "pistoseg_b200.ops.fuse_argmax_confusion_host -> pisto_fuse_argmax_confusion_host (pinned host buffers)"},
         "gpu_launches": launches,

@@ -8,5 +8,5 @@ timeout 300 $BCMD > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $BCMD > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches rc=$?"
 timeout 300 $BCMD > /dev/null 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fuse_stream -s 2 -c 1 -f -o gpurun_out/prof_fuse $BCMD > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fuse_filter -s 2 -c 1 -f -o gpurun_out/prof_fuse $BCMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
