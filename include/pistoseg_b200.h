@@ -212,6 +212,18 @@ int pisto_mosaic_gather(pisto_handle_t h, const uint8_t* pool_img /* HWC u8, til
                         int bg_label, uint8_t* img_out /* [N][S][S][3] */, uint8_t* mask_out /* [N][S][S] */,
                         pisto_stream_t stream);
 
+/* Planning of the per-cell decisions on the device (create_dataset.ipynb:291-321: source tile, RandomCrop origin, the
+ * "background area is smaller than 80 %" rejection loop).  Counter-based: cell (q, c) of mosaic i is a pure function of
+ * (seed, i, q, c) through Philox4x32-10, identical for any GPU count; mosaic k of the call has index
+ * first_index + k * index_stride (rank r of G: first_index = r, stride = G, as create_dataset.ipynb:554).
+ * integral / integral_off (both NULL: no rejection, BCSS) is the 16-bit summed-area table of the padded background masks
+ * built by pisto_mosaic_bg_integral: tile t occupies (ph+1)*(pw+1) entries at integral_off[t], ph = max(h, patch_size). */
+int pisto_mosaic_bg_integral(pisto_handle_t h, const uint8_t* pool_bg, const int64_t* pool_off, const int32_t* pool_hw,
+                             const int64_t* integral_off, int P, int patch_size, uint16_t* integral, pisto_stream_t stream);
+int pisto_mosaic_plan_cells(pisto_handle_t h, uint64_t seed, int64_t first_index, int64_t index_stride, int N, int patch_num,
+                            int patch_size, int P, const int32_t* pool_hw, const uint16_t* integral, const int64_t* integral_off,
+                            int bg_label, int max_tries, pisto_mosaic_cell_t* cells /* [N][4][patch_num^2] */, pisto_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, philox
 
 FLIP_NONE, FLIP_ROWS, FLIP_COLS, FLIP_BOTH = 0, 1, 2, 3   # cv2.flip codes none / 0 / 1 / -1
 
@@ -67,24 +67,45 @@ class TilePool:
             "off": torch.from_numpy(off).to(device), "hw": torch.from_numpy(hw).to(device),
             "label": torch.from_numpy(self.labels_host).to(device),
         }
-        self._bg_integral = None
+        self._integral_host, self._integral_dev = {}, {}
 
     def __len__(self):
         return len(self.hw_host)
 
-    def bg_value_sum(self, t, cy, cx, ps, bg_label=3):
-        """sum(tile_mask[tile_mask == 3]) of a crop (the reference's rejection statistic, create_dataset.ipynb:314),
-        in padded coordinates, via per-tile integral images."""
-        if self.bg_host is None:
-            return 0
-        if self._bg_integral is None:
-            self._bg_integral = {}
-        if t not in self._bg_integral:
-            from_pad = _pad_reflect101((self.bg_host[t] > 0).astype(np.int64), ps)
-            self._bg_integral[t] = np.pad(from_pad.cumsum(0).cumsum(1), ((1, 0), (1, 0)))
-        I = self._bg_integral[t]
-        n = I[cy + ps, cx + ps] - I[cy, cx + ps] - I[cy + ps, cx] + I[cy, cx]
-        return int(n) * bg_label
+    def integral_offsets(self, ps):
+        """Entry offset of every tile's (ph+1) x (pw+1) summed-area table, ph = max(h, ps)."""
+        ph, pw = np.maximum(self.hw_host[:, 0], ps).astype(np.int64), np.maximum(self.hw_host[:, 1], ps).astype(np.int64)
+        sz = (ph + 1) * (pw + 1)
+        ioff = np.zeros(len(sz), np.int64)
+        ioff[1:] = np.cumsum(sz[:-1])
+        return ioff, int(sz.sum())
+
+    def integral_host(self, ps):
+        """16-bit summed-area tables of (bg > 0) over the PadIfNeeded-padded tiles (numpy restatement of
+        bg_integral_kernel; modulo 2^16, which is exact for crops of fewer than 65536 pixels)."""
+        if ps not in self._integral_host:
+            ioff, total = self.integral_offsets(ps)
+            flat = np.zeros(total, np.uint16)
+            for t, b in enumerate(self.bg_host):
+                padded = _pad_reflect101((np.asarray(b) > 0).astype(np.int64), ps)
+                I = np.pad(padded.cumsum(0).cumsum(1), ((1, 0), (1, 0)))
+                flat[ioff[t]:ioff[t] + I.size] = (I & 0xFFFF).astype(np.uint16).reshape(-1)
+            self._integral_host[ps] = (ioff, flat)
+        return self._integral_host[ps]
+
+    def integral_device(self, ps):
+        """The same tables built on the device by pisto_mosaic_bg_integral (cached per patch size)."""
+        if ps not in self._integral_dev:
+            ioff, total = self.integral_offsets(ps)
+            device = self.dev["img"].device
+            dev = device.index if device.index is not None else torch.cuda.current_device()
+            ioff_d = torch.from_numpy(ioff).to(device)
+            integral = torch.empty(total, dtype=torch.int16, device=device)
+            lib = _lib.load()
+            _lib.check(lib.pisto_mosaic_bg_integral(_lib.handle(dev), ops._ptr(self.dev["bg"]), ops._ptr(self.dev["off"]), ops._ptr(self.dev["hw"]),
+                                                    ops._ptr(ioff_d), len(self), int(ps), ops._ptr(integral), ops._stream(dev)))
+            self._integral_dev[ps] = (ioff_d, integral)
+        return self._integral_dev[ps]
 
 
 def _pad_reflect101(a, ps):
@@ -103,62 +124,159 @@ def _pad_reflect101(a, ps):
     return a[refl(np.arange(-top, h + bottom), h)][:, refl(np.arange(-left, w + right), w)]
 
 
+KEY_CELLS, KEY_QUADS = 0xC3110000, 0x51AD0000   # xor-ed into the high key word: independent streams per purpose
+
+
 class MosaicPlanner:
-    """Decision table generator: plan(i) depends only on (seed, i)."""
+    """Decision tables of ``CropAndConcatDataset`` (create_dataset.ipynb:273-372): plan(i) depends only on (seed, i).
+
+    Per-cell decisions (source tile, crop origin, background rejection: 4 * patch_num^2 per mosaic) come from
+    ``pisto_mosaic_plan_cells`` on the device (``cells_device``) or from the identical numpy arithmetic (``cells_host``);
+    the per-quadrant decisions (split, flip, ShiftScaleRotate parameters -> inverse affine in float64, RandomCrop origin:
+    16 numbers per mosaic) are evaluated on the host, vectorised over mosaics, because their float64 trigonometry must be
+    the host's for the affine maps to equal cv2's bit for bit.
+    """
 
     def __init__(self, pool, patch_num, patch_size, seed=2022, reject_bg=False, bg_label=3,
-                 p_flip=0.8, p_warp=0.8, shift_limit=0.0625, scale_limit=0.2, rotate_limit=45.0):
-        self.pool, self.pn, self.ps, self.seed = pool, patch_num, patch_size, seed
-        self.reject_bg, self.bg_label = reject_bg, bg_label
+                 p_flip=0.8, p_warp=0.8, shift_limit=0.0625, scale_limit=0.2, rotate_limit=45.0, max_tries=64):
+        self.pool, self.pn, self.ps, self.seed = pool, patch_num, patch_size, int(seed)
+        self.reject_bg, self.bg_label, self.max_tries = bool(reject_bg) and pool.bg_host is not None, bg_label, max_tries
         self.p_flip, self.p_warp = p_flip, p_warp
         self.shift_limit, self.scale_limit, self.rotate_limit = shift_limit, scale_limit, rotate_limit
 
-    def plan(self, i):
-        rng = np.random.Generator(np.random.Philox(key=[self.seed, int(i)]))
-        pn, ps = self.pn, self.ps
-        H = W = pn * ps
-        plan = np.zeros((), PLAN_DTYPE)
-        cells = np.zeros((4, pn * pn), CELL_DTYPE)
-        for q in range(4):  # create_one_image x 4 (create_dataset.ipynb:283)
-            for c in range(pn * pn):
-                while True:
-                    t = int(rng.integers(0, len(self.pool)))
-                    th, tw = (int(v) for v in self.pool.hw_host[t])
-                    ph, pw = max(th, ps), max(tw, ps)
-                    # albumentations RandomCrop: y1 = int((H - h + 1) * r)
-                    cy = int((ph - ps + 1) * rng.random()); cx = int((pw - ps + 1) * rng.random())
-                    # "background area is smaller than 80 %" -- the reference sums label VALUES (3 per bg pixel)
-                    if not self.reject_bg or self.pool.bg_value_sum(t, cy, cx, ps, self.bg_label) < ps * ps * 0.8:
-                        break
-                cells[q, c] = (t, cy, cx)
-        h = int(H * (rng.random() * 0.6 + 0.2)); w = int(W * (rng.random() * 0.6 + 0.2))  # create_dataset.ipynb:336
+    def _keys(self, purpose):
+        return self.seed & 0xFFFFFFFF, ((self.seed >> 32) & 0xFFFFFFFF) ^ purpose
+
+    # ---- per-cell decisions ---------------------------------------------------------------------------------------
+    def cells_host(self, indices):
+        """[N, 4, pn^2] CELL_DTYPE, numpy restatement of plan_cells_kernel."""
+        idx = np.asarray(list(indices), np.uint64)
+        N, pn2, ps, P = len(idx), self.pn * self.pn, self.ps, len(self.pool)
+        k0, k1 = self._keys(KEY_CELLS)
+        ilo = np.repeat(idx & np.uint64(0xFFFFFFFF), 4 * pn2)
+        ihi = np.repeat(idx >> np.uint64(32), 4 * pn2)
+        slot = np.tile(np.arange(4 * pn2, dtype=np.uint64), N)
+        tile = np.zeros(N * 4 * pn2, np.int64); cy = np.zeros_like(tile); cx = np.zeros_like(tile)
+        pending = np.arange(N * 4 * pn2)
+        hw = self.pool.hw_host.astype(np.int64)
+        if self.reject_bg:
+            ioff, I = self.pool.integral_host(ps)
+        for t in range(self.max_tries):
+            r0, r1, r2, _ = philox.philox4x32_10(ilo[pending], ihi[pending], slot[pending], t, k0, k1)
+            tl = philox.mulhi(r0, P)
+            ph, pw = np.maximum(hw[tl, 0], ps), np.maximum(hw[tl, 1], ps)
+            y, x = philox.mulhi(r1, ph - ps + 1), philox.mulhi(r2, pw - ps + 1)
+            tile[pending], cy[pending], cx[pending] = tl, y, x
+            if not self.reject_bg:
+                break
+            W1 = pw + 1
+            base = ioff[tl]
+            n = (I[base + (y + ps) * W1 + x + ps].astype(np.int64) - I[base + y * W1 + x + ps] - I[base + (y + ps) * W1 + x] + I[base + y * W1 + x]) & 0xFFFF
+            pending = pending[10 * n * self.bg_label >= 8 * ps * ps]  # "background area is smaller than 80 %" fails: draw again
+            if len(pending) == 0:
+                break
+        cells = np.zeros((N, 4, pn2), CELL_DTYPE)
+        cells["tile"] = tile.reshape(N, 4, pn2); cells["cy"] = cy.reshape(N, 4, pn2); cells["cx"] = cx.reshape(N, 4, pn2)
+        return cells
+
+    def cells_device(self, first_index, index_stride, N):
+        """CUDA uint8 view of MosaicCell[N, 4, pn^2] for mosaics first_index + k * index_stride (pisto_mosaic_plan_cells)."""
+        device = self.pool.dev["img"].device
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        cells = torch.empty(N * 4 * self.pn * self.pn * CELL_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        ioff_d, integral = self.pool.integral_device(self.ps) if self.reject_bg else (None, None)
+        lib = _lib.load()
+        _lib.check(lib.pisto_mosaic_plan_cells(_lib.handle(dev), self.seed & 0xFFFFFFFFFFFFFFFF, int(first_index), int(index_stride), int(N), self.pn,
+                                               self.ps, len(self.pool), ops._ptr(self.pool.dev["hw"]), ops._ptr(integral), ops._ptr(ioff_d),
+                                               int(self.bg_label), int(self.max_tries), ops._ptr(cells), ops._stream(dev)))
+        return cells
+
+    # ---- per-quadrant decisions -----------------------------------------------------------------------------------
+    def quad_plans(self, indices):
+        """[N] PLAN_DTYPE: split, and per quadrant flip code, warp flag + inverse affine, crop origin."""
+        idx = np.asarray(list(indices), np.uint64)
+        N, H = len(idx), self.pn * self.ps
+        W = H
+        k0, k1 = self._keys(KEY_QUADS)
+        ilo, ihi = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+        plans = np.zeros(N, PLAN_DTYPE)
+        r = philox.philox4x32_10(ilo, ihi, 4, 0, k0, k1)
+        h = (H * (philox.u53(r[0], r[1]) * 0.6 + 0.2)).astype(np.int64)   # create_dataset.ipynb:336
+        w = (W * (philox.u53(r[2], r[3]) * 0.6 + 0.2)).astype(np.int64)
         h += h % 2; w += w % 2
-        plan["split_h"], plan["split_w"] = h, w
+        plans["split_h"], plans["split_w"] = h, w
         sizes = [(h, w), (h, W - w), (H - h, w), (H - h, W - w)]
         for q in range(4):
-            qd = plan["quad"][q]
-            qd["flip"] = int(rng.integers(1, 4)) if rng.random() < self.p_flip else FLIP_NONE  # albu.Flip: d in {-1, 0, 1}
-            if rng.random() < self.p_warp:
-                angle = rng.uniform(-self.rotate_limit, self.rotate_limit)
-                scale = rng.uniform(1 - self.scale_limit, 1 + self.scale_limit)
-                dx = rng.uniform(-self.shift_limit, self.shift_limit); dy = rng.uniform(-self.shift_limit, self.shift_limit)
-                qd["warp"] = 1
-                qd["minv"] = invert_affine(shift_scale_rotate_matrix(H, W, angle, scale, dx, dy)).reshape(-1)
+            rA = philox.philox4x32_10(ilo, ihi, q, 0, k0, k1)
+            rB = philox.philox4x32_10(ilo, ihi, q, 1, k0, k1)
+            rC = philox.philox4x32_10(ilo, ihi, q, 2, k0, k1)
+            rD = philox.philox4x32_10(ilo, ihi, q, 3, k0, k1)
+            flip = np.where(philox.u32(rA[0]) < self.p_flip, 1 + philox.mulhi(rA[1], 3), FLIP_NONE)   # albu.Flip: d in {-1, 0, 1}
+            warp = philox.u32(rA[2]) < self.p_warp
+            angle = -self.rotate_limit + 2 * self.rotate_limit * philox.u53(rB[0], rB[1])
+            scale = (1 - self.scale_limit) + 2 * self.scale_limit * philox.u53(rB[2], rB[3])
+            dx = -self.shift_limit + 2 * self.shift_limit * philox.u53(rC[0], rC[1])
+            dy = -self.shift_limit + 2 * self.shift_limit * philox.u53(rC[2], rC[3])
             hq, wq = sizes[q]
-            qd["crop_y"] = int((H - hq + 1) * rng.random()); qd["crop_x"] = int((W - wq + 1) * rng.random())
-        return plan, cells
+            qd = plans["quad"][:, q]
+            qd["flip"], qd["warp"] = flip, warp
+            qd["crop_y"] = ((H - hq + 1) * philox.u53(rD[0], rD[1])).astype(np.int64)   # albumentations RandomCrop
+            qd["crop_x"] = ((W - wq + 1) * philox.u53(rD[2], rD[3])).astype(np.int64)
+            minv = invert_affine_batch(shift_scale_rotate_batch(H, W, angle, scale, dx, dy))
+            qd["minv"] = np.where(warp[:, None], minv, 0.0)
+            plans["quad"][:, q] = qd
+        return plans
 
     def plans(self, indices):
-        ps, cs = zip(*(self.plan(i) for i in indices))
-        return np.stack(ps), np.stack(cs)
+        """(plans [N] PLAN_DTYPE, cells [N,4,pn^2] CELL_DTYPE) on the host."""
+        indices = list(indices)
+        return self.quad_plans(indices), self.cells_host(indices)
+
+    def plan(self, i):
+        p, c = self.plans([i])
+        return p[0], c[0]
+
+
+def shift_scale_rotate_batch(H, W, angle, scale, dx, dy):
+    """``shift_scale_rotate_matrix`` over arrays, same float64 operation order -> [N, 2, 3]."""
+    a = angle * (np.pi / 180.0)
+    alpha, beta = np.cos(a) * scale, np.sin(a) * scale
+    cx, cy = W / 2 - 0.5, H / 2 - 0.5
+    M = np.empty((len(a), 2, 3), np.float64)
+    M[:, 0, 0] = alpha; M[:, 0, 1] = beta; M[:, 0, 2] = (1 - alpha) * cx - beta * cy
+    M[:, 1, 0] = -beta; M[:, 1, 1] = alpha; M[:, 1, 2] = beta * cx + (1 - alpha) * cy
+    M[:, 0, 2] += dx * W
+    M[:, 1, 2] += dy * H
+    return M
+
+
+def invert_affine_batch(M):
+    """``invert_affine`` over [N, 2, 3], same float64 operation order -> [N, 6]."""
+    M = M.copy()
+    D = M[:, 0, 0] * M[:, 1, 1] - M[:, 0, 1] * M[:, 1, 0]
+    with np.errstate(divide="ignore"):
+        D = np.where(D != 0, 1.0 / D, 0.0)
+    A11, A22 = M[:, 1, 1] * D, M[:, 0, 0] * D
+    M[:, 0, 0] = A11; M[:, 0, 1] *= -D; M[:, 1, 0] *= -D; M[:, 1, 1] = A22
+    b1 = -M[:, 0, 0] * M[:, 0, 2] - M[:, 0, 1] * M[:, 1, 2]
+    b2 = -M[:, 1, 0] * M[:, 0, 2] - M[:, 1, 1] * M[:, 1, 2]
+    M[:, 0, 2] = b1; M[:, 1, 2] = b2
+    return M.reshape(len(M), 6)
 
 
 def synthesize(pool, plans, cells, patch_num, patch_size, bg_label=3):
-    """plans [N] PLAN_DTYPE, cells [N,4,pn*pn] CELL_DTYPE (numpy) -> (img u8 [N,S,S,3], mask u8 [N,S,S]) CUDA tensors."""
+    """plans [N] PLAN_DTYPE (numpy), cells [N,4,pn*pn] CELL_DTYPE (numpy) or the CUDA uint8 tensor of ``cells_device``
+    -> (img u8 [N,S,S,3], mask u8 [N,S,S]) CUDA tensors."""
     device = pool.dev["img"].device
     p = torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(-1)).to(device)
-    c = torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(device)
+    c = cells if torch.is_tensor(cells) else torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(device)
     return ops.mosaic_gather(pool.dev, p, c, patch_num, patch_size, bg_label)
+
+
+def synthesize_range(pool, planner, first_index, index_stride, N, bg_label=3):
+    """Mosaics first_index + k * index_stride, k < N: quadrant plans on the host (vectorised), cells on the device."""
+    idx = [first_index + k * index_stride for k in range(N)]
+    return synthesize(pool, planner.quad_plans(idx), planner.cells_device(first_index, index_stride, N), planner.pn, planner.ps, bg_label)
 
 
 def shard_indices(n_total, rank, world):

@@ -109,3 +109,33 @@ def test_mosaic_matches_cv2_fixtures(cuda, tag, pn, ps):
     img, msk = mosaic.synthesize(pool, plans, cells, pn, ps)
     assert np.array_equal(img.cpu().numpy(), z[f"{tag}_img"])
     assert np.array_equal(msk.cpu().numpy(), z[f"{tag}_mask"])
+
+
+@pytest.mark.parametrize("pn,ps,with_bg", [(4, 56, True), (2, 112, False), (7, 32, True)])
+def test_device_planner_equals_host_planner(cuda, pn, ps, with_bg):
+    """pisto_mosaic_plan_cells / pisto_mosaic_bg_integral == their numpy restatements, bit for bit; sharded generation
+    (first_index, stride) reproduces the same mosaics."""
+    rng = np.random.default_rng(pn * 7 + ps)
+    imgs, bgs, labels = make_pool(rng, 40, ps, with_bg)
+    if with_bg:  # make the rejection loop bite: half of the tiles are mostly background
+        for t in range(0, 40, 2):
+            bgs[t] = (rng.random(bgs[t].shape) < 0.9).astype(np.uint8) * 255
+    pool = mosaic.TilePool(imgs, labels, bgs, device=cuda)
+    planner = mosaic.MosaicPlanner(pool, pn, ps, seed=77, reject_bg=with_bg)
+    if with_bg:
+        ioff, I = pool.integral_host(ps)
+        ioff_d, I_d = pool.integral_device(ps)
+        assert np.array_equal(I_d.cpu().numpy().view(np.uint16), I)
+    N = 16
+    host = planner.cells_host(range(5, 5 + 3 * N, 3))
+    dev = planner.cells_device(5, 3, N).cpu().numpy().view(mosaic.CELL_DTYPE).reshape(N, 4, pn * pn)
+    assert np.array_equal(dev, host)
+    if with_bg:
+        assert not np.array_equal(host, mosaic.MosaicPlanner(pool, pn, ps, seed=77, reject_bg=False).cells_host(range(5, 5 + 3 * N, 3)))
+    img, msk = mosaic.synthesize_range(pool, planner, 5, 3, N)
+    p, c = planner.plans(range(5, 5 + 3 * N, 3))
+    img2, msk2 = mosaic.synthesize(pool, p, c, pn, ps)
+    assert torch.equal(img, img2) and torch.equal(msk, msk2)
+    # 64-bit mosaic indices
+    big = planner.cells_device(2 ** 33 + 1, 1, 2).cpu().numpy().view(mosaic.CELL_DTYPE).reshape(2, 4, pn * pn)
+    assert np.array_equal(big, planner.cells_host([2 ** 33 + 1, 2 ** 33 + 2]))

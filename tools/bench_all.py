@@ -108,11 +108,19 @@ bgs = [(rng.random((224, 224)) < 0.1).astype(np.uint8) * 255 for _ in range(64)]
 bgs = [bgs[i % 64] for i in range(P)]
 pool = mosaic.TilePool(imgs, rng.integers(0, 3, P).astype(np.uint8), bgs, device=dev)
 for pn, ps in ((4, 56), (2, 112), (7, 32)):
-    planner = mosaic.MosaicPlanner(pool, pn, ps, reject_bg=False)
-    t0 = time.perf_counter(); plans, cells = planner.plans(range(512)); plan_s = time.perf_counter() - t0
-    reps = 16
-    plans = np.tile(plans, reps); cells = np.tile(cells, (reps, 1, 1))
-    pl = torch.from_numpy(plans.view(np.uint8).reshape(-1)).to(dev); ce = torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(dev)
-    ms = timeit(lambda: ops.mosaic_gather(pool.dev, pl, ce, pn, ps, 3), 5)
-    emit(f"mosaic_gather {pn}x{ps} (224x224 image+mask, 80% warped quadrants)", len(plans), "mosaics", ms, 2 * (224 * 224 * 4), host_plan_us_per_mosaic=plan_s / 512 * 1e6)
+    planner = mosaic.MosaicPlanner(pool, pn, ps, reject_bg=True)
+    N = 8192
+    t0 = time.perf_counter(); plans = planner.quad_plans(range(N)); quad_s = time.perf_counter() - t0
+    pool.integral_device(ps)
+    cells = planner.cells_device(0, 1, N)
+    ms_cells = timeit(lambda: planner.cells_device(0, 1, N), 5)
+    pl = torch.from_numpy(plans.view(np.uint8).reshape(-1)).to(dev)
+    ms = timeit(lambda: ops.mosaic_gather(pool.dev, pl, cells, pn, ps, 3), 5)
+    emit(f"mosaic_gather {pn}x{ps} (224x224 image+mask, 80% warped quadrants)", N, "mosaics", ms, 2 * (224 * 224 * 4),
+         plan_cells_device_us_per_mosaic=ms_cells / N * 1e3, plan_quads_host_us_per_mosaic=quad_s / N * 1e6)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for r in range(3):
+        mosaic.synthesize_range(pool, planner, r * N, 1, N)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
+    emit(f"mosaic end to end {pn}x{ps}: host quadrant plans + device cell plans + gather (wall clock)", N, "mosaics", dt * 1e3, 2 * (224 * 224 * 4))
 fout.close()
