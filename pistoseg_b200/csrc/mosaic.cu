@@ -51,105 +51,140 @@ __device__ __forceinline__ int cv_round(double v) {
   return (int)r;
 }
 
-struct SrcPix { long long off; int t; };  // pixel offset into the pool (pool_off[t] + ty*tw + tx), tile id
+// Per-mosaic tables in shared memory: the plan (272 B) and one entry per grid cell of the 4 composites with everything a
+// pixel fetch needs (no dependent global loads on the pixel path: cells -> pool_hw -> pool_off used to be a chain of three).
+struct CellEnt {
+  long long base;        // pool pixel offset of crop pixel (0, 0): pool_off[t] + (cy - pad_t) * tw + (cx - pad_l)
+  int tw, th;            // tile size
+  short cye, cxe;        // crop origin in UNPADDED tile coordinates (negative inside the PadIfNeeded border)
+  unsigned char label;   // pool_label[t]
+  unsigned char padded;  // tile smaller than the patch: REFLECT_101 fix-up needed
+  short pad_;
+};
 
-// composite coordinate (after flip) -> pool pixel.  PS > 0: patch size known at compile time (division by constant).
+// composite coordinate (after flip) -> pool pixel offset; *label gets the tile's class
 template <int PS>
-__device__ __forceinline__ SrcPix composite_src(const MosaicParams& p, const pisto_mosaic_cell_t* cells_q, int flip, int y, int x) {
-  const int ps = PS > 0 ? PS : p.ps;
-  if (flip & 1) y = p.S - 1 - y;   // cv2.flip code 0 / -1: rows reversed
-  if (flip & 2) x = p.S - 1 - x;   // cv2.flip code 1 / -1: cols reversed
+__device__ __forceinline__ long long composite_src(const CellEnt* ents_q, int S, int pn, int ps_rt, int flip, int y, int x, unsigned int* label) {
+  const int ps = PS > 0 ? PS : ps_rt;
+  if (flip & 1) y = S - 1 - y;   // cv2.flip code 0 / -1: rows reversed
+  if (flip & 2) x = S - 1 - x;   // cv2.flip code 1 / -1: cols reversed
   const int cr = y / ps, cc = x / ps;
   const int iy = y - cr * ps, ix = x - cc * ps;
-  const pisto_mosaic_cell_t cell = cells_q[cr * p.pn + cc];
-  const int2 hw = __ldg(reinterpret_cast<const int2*>(p.pool_hw) + cell.tile);
-  const int th = hw.x, tw = hw.y;
-  int ty = cell.cy + iy, tx = cell.cx + ix;
-  if (th < ps || tw < ps) {  // PadIfNeeded: centred REFLECT_101 pad (rare)
-    const int pad_t = th < ps ? (ps - th) >> 1 : 0;   // int((ps - th) / 2.0)
-    const int pad_l = tw < ps ? (ps - tw) >> 1 : 0;
-    ty = reflect101(ty - pad_t, th);
-    tx = reflect101(tx - pad_l, tw);
-  }
-  SrcPix s;
-  s.t = cell.tile;
-  s.off = p.pool_off[cell.tile] + (long long)ty * tw + tx;
-  return s;
+  const CellEnt e = ents_q[cr * pn + cc];
+  if (label) *label = e.label;
+  if (!e.padded) return e.base + iy * e.tw + ix;
+  // PadIfNeeded: centred REFLECT_101 pad (rare)
+  const int ty = reflect101(e.cye + iy, e.th), tx = reflect101(e.cxe + ix, e.tw);
+  return e.base - ((long long)e.cye * e.tw + e.cxe) + (long long)ty * e.tw + tx;
 }
 
+// One CTA per mosaic (grid-stride over mosaics); a thread produces 4 consecutive output pixels per step.
 template <int PS>
 __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant__ MosaicParams p) {
-  const int S = p.S;
+  extern __shared__ __align__(16) unsigned char msm[];
+  pisto_mosaic_plan_t* plan = reinterpret_cast<pisto_mosaic_plan_t*>(msm);
+  CellEnt* ents = reinterpret_cast<CellEnt*>(msm + ((sizeof(pisto_mosaic_plan_t) + 15) & ~15u));
+  const int S = p.S, pn = p.pn, pn2 = pn * pn;
+  // fixed-point affine terms of OpenCV's WarpAffineInvoker, per quadrant: colt[q][x] = {adelta, bdelta} of composite column x,
+  // rowt[q][y] = {X0, Y0} of composite row y (float64 evaluation, left-to-right products, round-half-even) -- evaluated once
+  // per (quadrant, row / column) instead of once per pixel
+  int2* colt = reinterpret_cast<int2*>(ents + 4 * pn2);
+  int2* rowt = colt + 4 * S;
+  const int ps = PS > 0 ? PS : p.ps;
   const int groups_per_row = S / 4;
-  const long long total = (long long)p.N * S * groups_per_row;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int gx = (int)(idx % groups_per_row);
-    const long long t = idx / groups_per_row;
-    const int Y = (int)(t % S);
-    const int n = (int)(t / S);
-    const pisto_mosaic_plan_t* plan = p.plans + n;
-    const int sh = plan->split_h, sw = plan->split_w;
-    unsigned int img_bytes[12];
-    unsigned int mask_bytes[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int X = gx * 4 + k;
-      const int q = (Y >= sh ? 2 : 0) + (X >= sw ? 1 : 0);
+  const int items = S * groups_per_row;
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    __syncthreads();  // the previous mosaic's tables are no longer read
+    for (int i = threadIdx.x; i < (int)(sizeof(pisto_mosaic_plan_t) / 4); i += blockDim.x)
+      reinterpret_cast<uint32_t*>(plan)[i] = reinterpret_cast<const uint32_t*>(p.plans + n)[i];
+    for (int i = threadIdx.x; i < 4 * pn2; i += blockDim.x) {
+      const pisto_mosaic_cell_t c = p.cells[(long long)n * 4 * pn2 + i];
+      const int2 hw = __ldg(reinterpret_cast<const int2*>(p.pool_hw) + c.tile);
+      const int th = hw.x, tw = hw.y;
+      const int pad_t = th < ps ? (ps - th) >> 1 : 0;   // int((ps - th) / 2.0)
+      const int pad_l = tw < ps ? (ps - tw) >> 1 : 0;
+      CellEnt e;
+      e.tw = tw; e.th = th;
+      e.cye = (short)(c.cy - pad_t); e.cxe = (short)(c.cx - pad_l);
+      e.base = p.pool_off[c.tile] + (long long)e.cye * tw + e.cxe;
+      e.label = p.pool_label[c.tile];
+      e.padded = (th < ps || tw < ps) ? 1 : 0;
+      e.pad_ = 0;
+      ents[i] = e;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * S; i += blockDim.x) {
+      const int q = i / S, c = i - q * S;
       const pisto_mosaic_quad_t* qd = &plan->quad[q];
-      const pisto_mosaic_cell_t* cells_q = p.cells + ((long long)n * 4 + q) * p.pn * p.pn;
-      const int yc = (Y >= sh ? Y - sh : Y) + qd->crop_y;
-      const int xc = (X >= sw ? X - sw : X) + qd->crop_x;
-      const int flip = qd->flip;
-      if (!qd->warp) {
-        SrcPix s = composite_src<PS>(p, cells_q, flip, yc, xc);
-        const uint8_t* px = p.pool_img + 3 * s.off;
-        img_bytes[3 * k + 0] = px[0]; img_bytes[3 * k + 1] = px[1]; img_bytes[3 * k + 2] = px[2];
-        unsigned int m = p.pool_label[s.t];
-        if (p.pool_bg && p.pool_bg[s.off] > 0) m = p.bg_label;
-        mask_bytes[k] = m;
-      } else {
-        const double m0 = qd->minv[0], m1 = qd->minv[1], m2 = qd->minv[2], m3 = qd->minv[3], m4 = qd->minv[4], m5 = qd->minv[5];
-        // OpenCV WarpAffineInvoker: adelta/bdelta per column, X0/Y0 per row (all float64, left-to-right products)
-        const int adelta = cv_round(__dmul_rn(__dmul_rn(m0, (double)xc), 1024.0));
-        const int bdelta = cv_round(__dmul_rn(__dmul_rn(m3, (double)xc), 1024.0));
-        const int X0b = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)yc), m2), 1024.0));
-        const int Y0b = cv_round(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)yc), m5), 1024.0));
-        {  // INTER_NEAREST (mask): round_delta = AB_SCALE / 2
-          const int sx = sat_short((X0b + 512 + adelta) >> AB_BITS);
-          const int sy = sat_short((Y0b + 512 + bdelta) >> AB_BITS);
-          SrcPix s = composite_src<PS>(p, cells_q, flip, reflect101(sy, S), reflect101(sx, S));
-          unsigned int m = p.pool_label[s.t];
-          if (p.pool_bg && p.pool_bg[s.off] > 0) m = p.bg_label;
-          mask_bytes[k] = m;
-        }
-        {  // INTER_LINEAR (image): round_delta = AB_SCALE / INTER_TAB_SIZE / 2 = 16
-          const int Xl = (X0b + 16 + adelta) >> (AB_BITS - INTER_BITS);
-          const int Yl = (Y0b + 16 + bdelta) >> (AB_BITS - INTER_BITS);
-          const int sx = sat_short(Xl >> INTER_BITS), sy = sat_short(Yl >> INTER_BITS);
-          const int fx = Xl & 31, fy = Yl & 31;
-          // 2x2 int16 weights of OpenCV's BilinearTab_i (closed form; the one saturated entry gets its fix-up)
-          int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-          if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
-          const int x0r = reflect101(sx, S), x1r = reflect101(sx + 1, S), y0r = reflect101(sy, S), y1r = reflect101(sy + 1, S);
-          const uint8_t* p00 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y0r, x0r).off;
-          const uint8_t* p01 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y0r, x1r).off;
-          const uint8_t* p10 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y1r, x0r).off;
-          const uint8_t* p11 = p.pool_img + 3 * composite_src<PS>(p, cells_q, flip, y1r, x1r).off;
+      if (qd->warp) {
+        const double v = (double)c;
+        colt[i] = make_int2(cv_round(__dmul_rn(__dmul_rn(qd->minv[0], v), 1024.0)), cv_round(__dmul_rn(__dmul_rn(qd->minv[3], v), 1024.0)));
+        rowt[i] = make_int2(cv_round(__dmul_rn(__dadd_rn(__dmul_rn(qd->minv[1], v), qd->minv[2]), 1024.0)),
+                            cv_round(__dmul_rn(__dadd_rn(__dmul_rn(qd->minv[4], v), qd->minv[5]), 1024.0)));
+      }
+    }
+    __syncthreads();
+    const int sh = plan->split_h, sw = plan->split_w;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int Y = it / groups_per_row, gx = it - Y * groups_per_row;
+      unsigned int img_bytes[12];
+      unsigned int mask_bytes[4];
 #pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            int v = (int)p00[ch] * w00 + (int)p01[ch] * w01 + (int)p10[ch] * w10 + (int)p11[ch] * w11;
-            v = (v + (1 << 14)) >> 15;
-            img_bytes[3 * k + ch] = (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      for (int k = 0; k < 4; k++) {
+        const int X = gx * 4 + k;
+        const int q = (Y >= sh ? 2 : 0) + (X >= sw ? 1 : 0);
+        const pisto_mosaic_quad_t* qd = &plan->quad[q];
+        const CellEnt* ents_q = ents + q * pn2;
+        const int yc = (Y >= sh ? Y - sh : Y) + qd->crop_y;
+        const int xc = (X >= sw ? X - sw : X) + qd->crop_x;
+        const int flip = qd->flip;
+        if (!qd->warp) {
+          unsigned int m;
+          const long long off = composite_src<PS>(ents_q, S, pn, ps, flip, yc, xc, &m);
+          const uint8_t* px = p.pool_img + 3 * off;
+          img_bytes[3 * k + 0] = px[0]; img_bytes[3 * k + 1] = px[1]; img_bytes[3 * k + 2] = px[2];
+          if (p.pool_bg && p.pool_bg[off] > 0) m = p.bg_label;
+          mask_bytes[k] = m;
+        } else {
+          const int2 cd = colt[q * S + xc], rd = rowt[q * S + yc];
+          const int adelta = cd.x, bdelta = cd.y, X0b = rd.x, Y0b = rd.y;
+          {  // INTER_NEAREST (mask): round_delta = AB_SCALE / 2
+            const int sx = sat_short((X0b + 512 + adelta) >> AB_BITS);
+            const int sy = sat_short((Y0b + 512 + bdelta) >> AB_BITS);
+            unsigned int m;
+            const long long off = composite_src<PS>(ents_q, S, pn, ps, flip, reflect101(sy, S), reflect101(sx, S), &m);
+            if (p.pool_bg && p.pool_bg[off] > 0) m = p.bg_label;
+            mask_bytes[k] = m;
+          }
+          {  // INTER_LINEAR (image): round_delta = AB_SCALE / INTER_TAB_SIZE / 2 = 16
+            const int Xl = (X0b + 16 + adelta) >> (AB_BITS - INTER_BITS);
+            const int Yl = (Y0b + 16 + bdelta) >> (AB_BITS - INTER_BITS);
+            const int sx = sat_short(Xl >> INTER_BITS), sy = sat_short(Yl >> INTER_BITS);
+            const int fx = Xl & 31, fy = Yl & 31;
+            // 2x2 int16 weights of OpenCV's BilinearTab_i (closed form; the one saturated entry gets its fix-up)
+            int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+            if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+            const int x0r = reflect101(sx, S), x1r = reflect101(sx + 1, S), y0r = reflect101(sy, S), y1r = reflect101(sy + 1, S);
+            const uint8_t* p00 = p.pool_img + 3 * composite_src<PS>(ents_q, S, pn, ps, flip, y0r, x0r, nullptr);
+            const uint8_t* p01 = p.pool_img + 3 * composite_src<PS>(ents_q, S, pn, ps, flip, y0r, x1r, nullptr);
+            const uint8_t* p10 = p.pool_img + 3 * composite_src<PS>(ents_q, S, pn, ps, flip, y1r, x0r, nullptr);
+            const uint8_t* p11 = p.pool_img + 3 * composite_src<PS>(ents_q, S, pn, ps, flip, y1r, x1r, nullptr);
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+              int v = (int)p00[ch] * w00 + (int)p01[ch] * w01 + (int)p10[ch] * w10 + (int)p11[ch] * w11;
+              v = (v + (1 << 14)) >> 15;
+              img_bytes[3 * k + ch] = (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
           }
         }
       }
-    }
-    uint32_t* io = reinterpret_cast<uint32_t*>(p.img_out + ((long long)(n * (long long)S + Y) * S + gx * 4) * 3);
+      uint32_t* io = reinterpret_cast<uint32_t*>(p.img_out + ((long long)(n * (long long)S + Y) * S + gx * 4) * 3);
 #pragma unroll
-    for (int wd = 0; wd < 3; wd++)
-      io[wd] = img_bytes[4 * wd] | (img_bytes[4 * wd + 1] << 8) | (img_bytes[4 * wd + 2] << 16) | (img_bytes[4 * wd + 3] << 24);
-    uint32_t* mo = reinterpret_cast<uint32_t*>(p.mask_out + (long long)(n * (long long)S + Y) * S + gx * 4);
-    *mo = mask_bytes[0] | (mask_bytes[1] << 8) | (mask_bytes[2] << 16) | (mask_bytes[3] << 24);
+      for (int wd = 0; wd < 3; wd++)
+        io[wd] = img_bytes[4 * wd] | (img_bytes[4 * wd + 1] << 8) | (img_bytes[4 * wd + 2] << 16) | (img_bytes[4 * wd + 3] << 24);
+      uint32_t* mo = reinterpret_cast<uint32_t*>(p.mask_out + (long long)(n * (long long)S + Y) * S + gx * 4);
+      *mo = mask_bytes[0] | (mask_bytes[1] << 8) | (mask_bytes[2] << 16) | (mask_bytes[3] << 24);
+    }
   }
 }
 
@@ -171,17 +206,22 @@ extern "C" int pisto_mosaic_gather(pisto_handle_t h, const uint8_t* pool_img, co
   p.pool_img = pool_img; p.pool_bg = pool_bg; p.pool_off = (const long long*)pool_off; p.pool_hw = pool_hw; p.pool_label = pool_label;
   p.plans = plans; p.cells = cells; p.N = N; p.pn = patch_num; p.ps = patch_size; p.S = S; p.bg_label = bg_label;
   p.img_out = img_out; p.mask_out = mask_out;
-  long long total = (long long)N * S * (S / 4);
-  long long grid = (total + kThreads - 1) / kThreads;
-  long long cap = (long long)h->sm_count * 16;
-  if (grid > cap) grid = cap;
+  const size_t smem = ((sizeof(pisto_mosaic_plan_t) + 15) & ~(size_t)15) + sizeof(CellEnt) * 4 * (size_t)patch_num * patch_num + 2 * sizeof(int2) * 4 * (size_t)S;
+  PISTO_REQUIRE(smem <= 200 * 1024, "pisto_mosaic_gather: patch_num %d too large for the per-mosaic cell table", patch_num);
+  int grid = N < h->sm_count * 8 ? N : h->sm_count * 8;
   cudaStream_t st = (cudaStream_t)stream;
+#define PISTO_MOSAIC_LAUNCH(PS_)                                                                                        \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) PISTO_CUDA(cudaFuncSetAttribute(mosaic_kernel<PS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mosaic_kernel<PS_><<<grid, kThreads, smem, st>>>(p);                                                               \
+  } while (0)
   switch (patch_size) {
-    case 32: mosaic_kernel<32><<<(int)grid, kThreads, 0, st>>>(p); break;
-    case 56: mosaic_kernel<56><<<(int)grid, kThreads, 0, st>>>(p); break;
-    case 112: mosaic_kernel<112><<<(int)grid, kThreads, 0, st>>>(p); break;
-    default: mosaic_kernel<0><<<(int)grid, kThreads, 0, st>>>(p); break;
+    case 32: PISTO_MOSAIC_LAUNCH(32); break;
+    case 56: PISTO_MOSAIC_LAUNCH(56); break;
+    case 112: PISTO_MOSAIC_LAUNCH(112); break;
+    default: PISTO_MOSAIC_LAUNCH(0); break;
   }
+#undef PISTO_MOSAIC_LAUNCH
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   return PISTO_OK;
