@@ -212,6 +212,14 @@ int pisto_mosaic_gather(pisto_handle_t h, const uint8_t* pool_img /* HWC u8, til
                         int bg_label, uint8_t* img_out /* [N][S][S][3] */, uint8_t* mask_out /* [N][S][S] */,
                         pisto_stream_t stream);
 
+/* The same gather from a PACKED pool: one 32-bit word per source pixel, r | g << 8 | b << 16 | (bg > 0) << 24, built once per
+ * pool by pisto_mosaic_pack_pool.  Same bytes per pixel as image + mask (4), but every bilinear tap is one aligned load. */
+int pisto_mosaic_pack_pool(pisto_handle_t h, const uint8_t* pool_img, const uint8_t* pool_bg /* or NULL */, int64_t n_px,
+                           uint32_t* pool_rgba, pisto_stream_t stream);
+int pisto_mosaic_gather_packed(pisto_handle_t h, const uint32_t* pool_rgba, const int64_t* pool_off, const int32_t* pool_hw,
+                               const uint8_t* pool_label, const pisto_mosaic_plan_t* plans, const pisto_mosaic_cell_t* cells, int N,
+                               int patch_num, int patch_size, int bg_label, uint8_t* img_out, uint8_t* mask_out, pisto_stream_t stream);
+
 /* Planning of the per-cell decisions on the device (create_dataset.ipynb:291-321: source tile, RandomCrop origin, the
  * "background area is smaller than 80 %" rejection loop).  Counter-based: cell (q, c) of mosaic i is a pure function of
  * (seed, i, q, c) through Philox4x32-10, identical for any GPU count; mosaic k of the call has index

@@ -75,6 +75,8 @@ SYMBOLS = {
     "pisto_canvas_axpy": (_i, [_vp, _vp, _vp, _i64, _d, _vp]),
     "pisto_argmax_f64": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "pisto_mosaic_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pisto_mosaic_pack_pool": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "pisto_mosaic_gather_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pisto_mosaic_bg_integral": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pisto_mosaic_plan_cells": (_i, [_vp, C.c_uint64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }

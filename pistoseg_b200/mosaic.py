@@ -264,13 +264,13 @@ def invert_affine_batch(M):
     return M.reshape(len(M), 6)
 
 
-def synthesize(pool, plans, cells, patch_num, patch_size, bg_label=3):
+def synthesize(pool, plans, cells, patch_num, patch_size, bg_label=3, packed=True):
     """plans [N] PLAN_DTYPE (numpy), cells [N,4,pn*pn] CELL_DTYPE (numpy) or the CUDA uint8 tensor of ``cells_device``
     -> (img u8 [N,S,S,3], mask u8 [N,S,S]) CUDA tensors."""
     device = pool.dev["img"].device
     p = torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(-1)).to(device)
     c = cells if torch.is_tensor(cells) else torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(device)
-    return ops.mosaic_gather(pool.dev, p, c, patch_num, patch_size, bg_label)
+    return ops.mosaic_gather(pool.dev, p, c, patch_num, patch_size, bg_label, packed=packed)
 
 
 def synthesize_range(pool, planner, first_index, index_stride, N, bg_label=3):

@@ -273,9 +273,10 @@ def argmax_f64(scores, present=None, gt=None, bg_match=3, bg_label=3, conf=None,
     return out
 
 
-def mosaic_gather(pool, plans, cells, patch_num, patch_size, bg_label=3):
+def mosaic_gather(pool, plans, cells, patch_num, patch_size, bg_label=3, packed=True):
     """pool: dict(img u8 flat HWC, bg u8 flat or None, off int64 [P], hw int32 [P,2], label u8 [P]) of CUDA tensors;
     plans: CUDA uint8 view of MosaicPlan[N]; cells: CUDA uint8 view of MosaicCell[N,4,pn*pn].
+    packed=True gathers from the 32-bit packed copy of the pool (built on first use), packed=False from the planar buffers.
     Returns (img u8 [N,S,S,3], mask u8 [N,S,S])  (create_dataset.ipynb:273-372)."""
     dev = _dev_index(pool["img"])
     device = pool["img"].device
@@ -284,7 +285,15 @@ def mosaic_gather(pool, plans, cells, patch_num, patch_size, bg_label=3):
     img = torch.empty((N, S, S, 3), dtype=torch.uint8, device=device)
     mask = torch.empty((N, S, S), dtype=torch.uint8, device=device)
     lib = _lib.load()
-    _lib.check(lib.pisto_mosaic_gather(_lib.handle(dev), _ptr(pool["img"]), _ptr(pool.get("bg")), _ptr(pool["off"]), _ptr(pool["hw"]),
-                                       _ptr(pool["label"]), _ptr(plans), _ptr(cells), N, patch_num, patch_size, int(bg_label),
-                                       _ptr(img), _ptr(mask), _stream(dev)))
+    if packed:
+        if pool.get("rgba") is None:  # pack once per pool: r | g << 8 | b << 16 | (bg > 0) << 24
+            n_px = pool["img"].numel() // 3
+            pool["rgba"] = torch.empty(n_px, dtype=torch.int32, device=device)
+            _lib.check(lib.pisto_mosaic_pack_pool(_lib.handle(dev), _ptr(pool["img"]), _ptr(pool.get("bg")), n_px, _ptr(pool["rgba"]), _stream(dev)))
+        _lib.check(lib.pisto_mosaic_gather_packed(_lib.handle(dev), _ptr(pool["rgba"]), _ptr(pool["off"]), _ptr(pool["hw"]), _ptr(pool["label"]),
+                                                  _ptr(plans), _ptr(cells), N, patch_num, patch_size, int(bg_label), _ptr(img), _ptr(mask), _stream(dev)))
+    else:
+        _lib.check(lib.pisto_mosaic_gather(_lib.handle(dev), _ptr(pool["img"]), _ptr(pool.get("bg")), _ptr(pool["off"]), _ptr(pool["hw"]),
+                                           _ptr(pool["label"]), _ptr(plans), _ptr(cells), N, patch_num, patch_size, int(bg_label),
+                                           _ptr(img), _ptr(mask), _stream(dev)))
     return img, mask

@@ -74,6 +74,8 @@ def test_mosaic_bit_exact_vs_oracle(cuda, pn, ps, with_bg):
     idx = list(range(10))
     plans, cells = planner.plans(idx)
     img, msk = mosaic.synthesize(pool, plans, cells, pn, ps)
+    img_p, msk_p = mosaic.synthesize(pool, plans, cells, pn, ps, packed=False)   # planar pools: same pixels
+    assert torch.equal(img, img_p) and torch.equal(msk, msk_p)
     img, msk = img.cpu().numpy(), msk.cpu().numpy()
     for k in idx:
         ri, rm = oracle_synthesize(plans[k], cells[k], imgs, bgs, labels, pn, ps)
