@@ -33,6 +33,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Native libraries write banners to fd 1 (NCCL prints its version there when
+# NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private copy of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def bytes_per_tile(sizes, with_gt=False):
     """Algorithmic (compulsory) HBM bytes per tile, SURVEY.md 8(d): views + bg + label (+ gt) + 32x32 logits."""
     return 4 * C * sum(h * h for h in sizes) + T * T * (2 + int(with_gt)) + 4 * C * 32 * 32
@@ -130,7 +141,7 @@ def run_reference(args):
                          "sample": f"{n} tiles per step x {args.steps} steps; oracle/pipeline.py (literal torch-CPU restatement of infer_pseudo_masks.py:118-154, torch.set_num_threads({os.cpu_count()}))"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -270,7 +281,7 @@ def run_ours(args):
         v, dt = cpu_reference_run(args.cpu_tiles)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{args.cpu_tiles} tiles of the same workload, oracle/pipeline.py (torch-CPU restatement of infer_pseudo_masks.py:118-154), {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
