@@ -34,6 +34,25 @@ def test_confusion_bad_pred_counted(cuda):
     assert np.array_equal(conf.cpu().numpy(), np.eye(3, dtype=np.int64))
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 4])
+def test_confusion_all_byte_values(cuda, C):
+    """Every byte value in both arrays (ignore labels 255 / C, predictions >= C), sizes around the 32-pixel grouping."""
+    g = torch.Generator().manual_seed(40 + C)
+    for n in (31, 32, 33, 95, 4096 + 17, 1 << 20):
+        pred = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+        gt = torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8)
+        small = torch.rand(n, generator=g) < 0.7      # mostly plausible labels, some arbitrary bytes
+        pred = torch.where(small, pred % (C + 1), pred)
+        gt = torch.where(small, gt % (C + 2), gt)
+        conf = ops.new_confusion(C, cuda)
+        bad = ops.confusion_accumulate(pred.to(cuda), gt.to(cuda), conf)
+        p64, g64 = pred.numpy().astype(np.int64), gt.numpy().astype(np.int64)
+        ok = (g64 < C) & (p64 < C)
+        ref = np.bincount(g64[ok] * C + p64[ok], minlength=C * C).reshape(C, C)
+        assert np.array_equal(conf.cpu().numpy(), ref), (C, n)
+        assert int(bad.cpu()) == int(((g64 < C) & (p64 >= C)).sum())
+
+
 def test_confusion_full_size_property(cuda):
     """At BASELINE size (10k BCSS tiles = 5e8 px): total == number of valid px, row sums == gt histogram."""
     C, n = 4, 10_000 * 224 * 224
