@@ -2,9 +2,7 @@
 // Replaces interpolate_tensor (reference infer_pseudo_masks.py:89-90, segmentation_test.py:88-89,197) and the inline
 // calls of OEEM/classification/prepare_seg_inputs.py:116,131,137.  Same association as ATen.
 //
-// HBM-bound for up-sampling (output written once, input re-read through L1/L2).  One thread produces 4 consecutive
-// output pixels of one row (16-byte store for f32), the column lerp parameters are recomputed per pixel (cheap next
-// to the store), the row parameters once per thread.
+// HBM-bound for up-sampling (output written once, input re-read through L1/L2).
 #include "common.cuh"
 
 namespace {
@@ -31,37 +29,71 @@ __device__ __forceinline__ double fma_t(double a, double b, double c) { return _
 __device__ __forceinline__ float mul_t(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_t(double a, double b) { return __dmul_rn(a, b); }
 
+// One thread owns 4 adjacent output columns of one plane and streams down a strip of output rows.  The column lerp
+// parameters are computed once per thread; per source row the horizontally interpolated values of the thread's columns are
+// kept in registers (Ha: row i0, Hb: row i1) and only reloaded when the output row moves to another source-row pair, so an
+// output row costs 4 multiplies + 4 fused multiply-adds and one 16-byte (f32) / two 16-byte (f64) stores.  The expression
+// fma(ly0, fma(lx0, a, lx1*b), ly1 * fma(lx0, c, lx1*d)) and its rounding are unchanged.
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in, T* __restrict__ out, long long NC, int hi, int wi,
-                                                       int ho, int wo, T scale_h, T scale_w) {
+                                                       int ho, int wo, T scale_h, T scale_w, int strips, int rows_per_strip, int xblocks,
+                                                       int vec_ok) {
   constexpr int PX = 4;
-  const int wq = (wo + PX - 1) / PX;
-  const long long total = NC * ho * wq;
   const bool same_h = hi == ho, same_w = wi == wo;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int xq = (int)(idx % wq);
-    const long long t = idx / wq;
-    const int y = (int)(t % ho);
-    const long long nc = t / ho;
-    const LerpT<T> ly = src_index_t(scale_h, y, hi, same_h);
-    const T* r0 = in + (nc * hi + ly.i0) * wi;
-    const T* r1 = in + (nc * hi + ly.i1) * wi;
-    T* o = out + (nc * ho + y) * wo;
-    T res[PX];
+  const long long nblocks = NC * strips * xblocks;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int xb = (int)(blk % xblocks);
+    const long long t = blk / xblocks;
+    const int strip = (int)(t % strips);
+    const long long nc = t / strips;
+    const int x0 = (xb * (int)blockDim.x + (int)threadIdx.x) * PX;
+    if (x0 >= wo) continue;
+    LerpT<T> lx[PX];
 #pragma unroll
-    for (int k = 0; k < PX; k++) {
-      int x = xq * PX + k;
-      if (x < wo) {
-        const LerpT<T> lx = src_index_t(scale_w, x, wi, same_w);
-        T a = r0[lx.i0], b = r0[lx.i1], c = r1[lx.i0], d = r1[lx.i1];
-        T h0 = fma_t(lx.l0, a, mul_t(lx.l1, b));
-        T h1 = fma_t(lx.l0, c, mul_t(lx.l1, d));
-        res[k] = fma_t(ly.l0, h0, mul_t(ly.l1, h1));
+    for (int k = 0; k < PX; k++) lx[k] = src_index_t(scale_w, min(x0 + k, wo - 1), wi, same_w);
+    const T* plane = in + nc * (long long)hi * wi;
+    T Ha[PX], Hb[PX];
+    int p0 = -1, p1 = -1;
+    auto load_row = [&](int i, T (&H)[PX]) {
+      const T* r = plane + (long long)i * wi;
+#pragma unroll
+      for (int k = 0; k < PX; k++) H[k] = fma_t(lx[k].l0, __ldg(r + lx[k].i0), mul_t(lx[k].l1, __ldg(r + lx[k].i1)));
+    };
+    const int ys = strip * rows_per_strip, ye = min(ho, ys + rows_per_strip);
+    T* o = out + (nc * ho + ys) * (long long)wo + x0;
+    for (int y = ys; y < ye; y++, o += wo) {
+      const LerpT<T> ly = src_index_t(scale_h, y, hi, same_h);
+      if (ly.i0 != p0 || ly.i1 != p1) {
+        if (ly.i0 == p1 && p1 >= 0) {
+#pragma unroll
+          for (int k = 0; k < PX; k++) Ha[k] = Hb[k];
+        } else {
+          load_row(ly.i0, Ha);
+        }
+        if (ly.i1 == ly.i0) {
+#pragma unroll
+          for (int k = 0; k < PX; k++) Hb[k] = Ha[k];
+        } else {
+          load_row(ly.i1, Hb);
+        }
+        p0 = ly.i0; p1 = ly.i1;
+      }
+      T res[PX];
+#pragma unroll
+      for (int k = 0; k < PX; k++) res[k] = fma_t(ly.l0, Ha[k], mul_t(ly.l1, Hb[k]));
+      if (vec_ok) {
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(o) = make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]);
+        } else {
+          reinterpret_cast<double2*>(o)[0] = make_double2((double)res[0], (double)res[1]);
+          reinterpret_cast<double2*>(o)[1] = make_double2((double)res[2], (double)res[3]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PX; k++)
+          if (x0 + k < wo) o[k] = res[k];
       }
     }
-#pragma unroll
-    for (int k = 0; k < PX; k++)
-      if (xq * PX + k < wo) o[xq * PX + k] = res[k];
   }
 }
 
@@ -70,16 +102,26 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
 int pisto_upsample_launch(pisto_ctx* h, const void* in, void* out, long long NC, int hi, int wi, int ho, int wo, int dtype,
                           cudaStream_t st) {
   if (NC == 0) return PISTO_OK;
-  long long total = NC * ho * ((wo + 3) / 4);
-  long long grid = (total + 255) / 256;
-  long long cap = (long long)h->sm_count * 16;
-  if (grid > cap) grid = cap;
+  const int wq = (wo + 3) / 4;
+  const int threads = wq >= 256 ? 256 : ((wq + 31) / 32) * 32;
+  const int xblocks = (wq + threads - 1) / threads;
+  // enough blocks to fill the machine, strips as long as possible (every strip start reloads two source rows)
+  long long want = (long long)h->sm_count * 16;
+  int strips = (int)((want + NC * xblocks - 1) / (NC * xblocks));
+  if (strips < 1) strips = 1;
+  if (strips > ho) strips = ho;
+  int rows_per_strip = (ho + strips - 1) / strips;
+  strips = (ho + rows_per_strip - 1) / rows_per_strip;
+  long long nblocks = NC * strips * xblocks;
+  long long grid = nblocks < want ? nblocks : want;
+  const size_t esz = dtype == 0 ? 4 : 8;
+  const int vec_ok = (wo % 4 == 0) && (((uintptr_t)out & 15) == 0) && ((wo * esz) % 16 == 0);
   if (dtype == 0)
-    upsample_kernel<float><<<(int)grid, 256, 0, st>>>((const float*)in, (float*)out, NC, hi, wi, ho, wo, (float)hi / (float)ho,
-                                                      (float)wi / (float)wo);
+    upsample_kernel<float><<<(int)grid, threads, 0, st>>>((const float*)in, (float*)out, NC, hi, wi, ho, wo, (float)hi / (float)ho,
+                                                          (float)wi / (float)wo, strips, rows_per_strip, xblocks, vec_ok);
   else
-    upsample_kernel<double><<<(int)grid, 256, 0, st>>>((const double*)in, (double*)out, NC, hi, wi, ho, wo, (double)hi / (double)ho,
-                                                       (double)wi / (double)wo);
+    upsample_kernel<double><<<(int)grid, threads, 0, st>>>((const double*)in, (double*)out, NC, hi, wi, ho, wo, (double)hi / (double)ho,
+                                                           (double)wi / (double)wo, strips, rows_per_strip, xblocks, vec_ok);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   return PISTO_OK;
