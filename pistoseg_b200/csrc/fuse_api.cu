@@ -75,7 +75,11 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
   cudaStream_t st = (cudaStream_t)stream;
   PISTO_CUDA(cudaSetDevice(h->device));
   bool launched = false;
-  if (a->impl == 0 || a->impl == 3 || a->impl == 4) {
+  if (a->impl == 0) {  // one full-resolution view: pure streaming kernel
+    rc = pisto_launch_fuse_identity(h, p, st, &launched);
+    if (rc != PISTO_OK) return rc;
+  }
+  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4)) {
     rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : a->impl - 2, &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched && a->impl != 0) {

@@ -1,0 +1,131 @@
+// Identity-view fast path of pisto_fuse_argmax_confusion: ONE view that already has the output resolution and needs no
+// de-augmentation -- the shape of mIoUMask.forward (reference loss.py:55-67: softmax over the class axis of full-resolution
+// logits, argmax, confusion against the mask) and of the revise-mask post-processing (infer_revise_masks.py:137-143).
+// Nothing is interpolated, so the op is a pure stream: C float4 loads + one mask word per 4 pixels in, (optionally) 4 label
+// bytes out; the decision is pisto_decide (margin fast path, exact slow path) exactly as in every other fusion kernel.
+// HBM-bound: 4*C + 1 (+1 bg, +1 label) bytes per pixel.
+#include "fuse_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_constant__ FuseParams p) {
+  constexpr int BINS = C * C;
+  __shared__ unsigned int hist[BINS];
+  const bool do_conf = p.conf != nullptr && p.gt != nullptr;
+  for (int i = threadIdx.x; i < BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const ViewDev& vw = p.view[0];
+  const long long hw = (long long)p.T_h * p.T_w;
+  const long long q_per_tile = hw / 4;
+  const long long total = q_per_tile * p.N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long lo = 0, hi = 0;  // packed 8-bit counters (C <= 4), flushed before they can overflow
+  int pending = 0;
+  auto flush = [&]() {
+    if (C <= 4) {
+#pragma unroll
+      for (int b = 0; b < (C <= 4 ? BINS : 1); b++) {
+        unsigned int v = (unsigned int)(((b < 8 ? lo : hi) >> (8 * (b & 7))) & 0xffull);
+        v = __reduce_add_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&hist[b], v);
+      }
+    }
+    lo = hi = 0; pending = 0;
+  };
+  // all lanes of a warp run the same number of iterations (flush uses full-mask warp reductions)
+  const long long warp_base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  for (long long qb = warp_base; qb < total; qb += stride) {
+    const long long q = qb + (threadIdx.x & 31);
+    if (q < total) {
+      const int n = (int)(q / q_per_tile);
+      const long long r4 = (q - (long long)n * q_per_tile) * 4;   // first pixel of the group inside the tile
+      const TilePresence tp = pisto_tile_presence(p, n);
+      int lab[4];
+      if (tp.single >= 0) {
+        lab[0] = lab[1] = lab[2] = lab[3] = tp.single;
+      } else {
+        const float* base = vw.logits + (long long)n * vw.tile_stride + r4;
+        float4 v[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
+        float a[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) a[c] = v[c].x;
+        lab[0] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+#pragma unroll
+        for (int c = 0; c < C; c++) a[c] = v[c].y;
+        lab[1] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+#pragma unroll
+        for (int c = 0; c < C; c++) a[c] = v[c].z;
+        lab[2] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+#pragma unroll
+        for (int c = 0; c < C; c++) a[c] = v[c].w;
+        lab[3] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+      }
+      const long long pix = (long long)n * hw + r4;
+      if (do_conf) {
+        const unsigned int g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const unsigned int gg = (g4 >> (8 * j)) & 0xffu;
+          if (gg < (unsigned)C) {
+            const unsigned int bn = gg * C + lab[j];
+            if (C <= 4) {
+              const unsigned long long inc = 1ull << (8 * (bn & 7));
+              if (bn < 8) lo += inc; else hi += inc;
+            } else {
+              atomicAdd(&hist[bn], 1u);
+            }
+          }
+        }
+      }
+      if (p.label_out) {
+        unsigned int o = (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+        if (p.bg) {
+          const unsigned int eq = __vcmpeq4(__ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix)), 0x01010101u * (unsigned)p.bg_match);
+          o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
+        }
+        *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
+      }
+    }
+    pending += 4;
+    if (do_conf && pending > 255 - 4) flush();
+  }
+  if (do_conf) {
+    flush();
+    __syncthreads();
+    for (int i = threadIdx.x; i < BINS; i += blockDim.x)
+      if (hist[i]) atomicAdd(&p.conf[i], (unsigned long long)hist[i]);
+  }
+}
+
+}  // namespace
+
+int pisto_launch_fuse_identity(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  *launched = false;
+  if (p.V != 1 || p.fuse_mode != PISTO_FUSE_LOGIT_MEAN) return PISTO_OK;
+  if (p.fused_out || p.entropy_out || p.lowres_out) return PISTO_OK;
+  const ViewDev& vw = p.view[0];
+  const ViewMap& m = vw.map;
+  if (!(vw.same_h && vw.same_w && m.a0 == 0 && m.ai == 1 && m.aj == 0 && m.b0 == 0 && m.bi == 0 && m.bj == 1)) return PISTO_OK;
+  const long long hw = (long long)p.T_h * p.T_w;
+  if (hw % 4 || vw.tile_stride % 4) return PISTO_OK;
+  if (((uintptr_t)vw.logits & 15) || (((uintptr_t)p.label_out | (uintptr_t)p.bg | (uintptr_t)p.gt) & 3)) return PISTO_OK;
+  const long long total = hw / 4 * p.N;
+  long long grid = (total + kThreads - 1) / kThreads;
+  const long long cap = (long long)h->sm_count * 16;
+  if (grid > cap) grid = cap;
+  switch (p.C) {
+#define PISTO_ID_CASE(CC) case CC: fuse_identity_kernel<CC><<<(int)grid, kThreads, 0, st>>>(p); break;
+    PISTO_ID_CASE(1) PISTO_ID_CASE(2) PISTO_ID_CASE(3) PISTO_ID_CASE(4) PISTO_ID_CASE(5) PISTO_ID_CASE(6) PISTO_ID_CASE(7) PISTO_ID_CASE(8)
+#undef PISTO_ID_CASE
+    default: return PISTO_OK;
+  }
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
+  *launched = true;
+  return PISTO_OK;
+}

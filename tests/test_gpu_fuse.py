@@ -213,3 +213,25 @@ def test_empty_and_errors(cuda):
         ops.fuse_argmax_confusion([torch.zeros((1, 3, 28, 28))], [0], (224, 224))  # CPU tensor: no fallback
     with pytest.raises(PistoError):
         ops.fuse_argmax_confusion([torch.zeros((1, 9, 28, 28), device=cuda)], [0], (224, 224))  # C > 8
+
+
+@pytest.mark.parametrize("C", [2, 3, 4, 5])
+def test_identity_view_fast_path_equals_generic(cuda, C):
+    """One full-resolution view (mIoUMask.forward / revise masks): the streaming identity kernel (automatic dispatch) and the
+    generic kernel agree on labels and confusion for every mask / decide mode, with ties, NaN and a strided channel slice."""
+    g = torch.Generator().manual_seed(100 + C)
+    N, T = 7, 64
+    x = torch.round(torch.randn((N, C + 1, T, T), generator=g) * 4) / 4   # quarter steps: plenty of exact ties
+    x[1, 1, 3, 5] = float("nan"); x[2, 2, 0, 0] = float("inf")
+    present = synthetic.make_present(N, C, 7, single_frac=0.3)
+    gt = torch.randint(0, C + 1, (N, T, T), generator=g, dtype=torch.uint8)
+    bg = (torch.rand((N, T, T), generator=g) < 0.2).to(torch.uint8)
+    xg = x.to(cuda)
+    for view in (xg[:, 1:], xg[:, :C].contiguous()):
+        for mask in (MASK_NONE, MASK_FILL, MASK_NEG_INF, MASK_MULTIPLY):
+            for decide in (DECIDE_RAW, DECIDE_SOFTMAX):
+                kw = dict(mask_mode=mask, decide=decide, present=present if mask != MASK_NONE else None, bg=bg, bg_match=1, bg_label=C, gt=gt)
+                a = ops.fuse_argmax_confusion([view], [0], (T, T), conf=ops.new_confusion(C, cuda), **kw)
+                b = ops.fuse_argmax_confusion([view], [0], (T, T), conf=ops.new_confusion(C, cuda), impl=IMPL_GENERIC, **kw)
+                assert torch.equal(a["labels"], b["labels"]), (C, mask, decide)
+                assert torch.equal(a["conf"], b["conf"]), (C, mask, decide)
