@@ -8,9 +8,6 @@ int pisto_launch_filter_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, i
 // np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch)
 int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   *launched = false;
-  // Four classes all in play means three difference fields per pixel pair: that variant does not fit the register file next to
-  // four column per thread (measured slower than the exact streaming kernel), so automatic dispatch leaves it to that kernel.
-  if (np == 0 && p.C == 4 && p.dec.mask_mode == PISTO_MASK_NONE) return PISTO_OK;
   if (p.fuse_mode != PISTO_FUSE_LOGIT_MEAN) return PISTO_OK;       // softmax per view is not linear
   if (p.fused_out || p.entropy_out) return PISTO_OK;               // full-resolution scores wanted: exact kernels
   if (p.dec.mask_mode == PISTO_MASK_MULTIPLY) return PISTO_OK;     // masked classes take part in the argmax

@@ -55,6 +55,7 @@ struct FilterGeom {
   int group_of[PISTO_MAX_VIEWS];
   int first_in_group[PISTO_MAX_VIEWS];
   int buf_floats;
+  int nbuf;                            // staging buffers: 2, or 1 (views released after the pre-pass, exact pass reads global memory)
   int g_ho[kFMaxGroups], g_wo[kFMaxGroups], g_same_w[kFMaxGroups];
   float g_scale_h[kFMaxGroups], g_scale_w[kFMaxGroups];
   int g_ybytes[kFMaxGroups];           // byte offset of group g's first difference map inside the Y area
@@ -446,7 +447,7 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
   return mxf;
 }
 
-template <int C, int V, int G, int F, int NP, bool LSM>
+template <int C, int V, int G, int F, int NP, bool LSM, int NB>
 __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __grid_constant__ FuseParams p,
                                                                       const __grid_constant__ FilterGeom g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -564,8 +565,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       int next = atomicAdd(g.counter, 1);
       bool next_views = next < p.N && tile_needs_views(next);
       for (int k = 0;; k++) {
-        const int b = k & 1;
-        if (k >= 2) mbar_wait_sleep(&ctl->empty[b], ((k >> 1) - 1) & 1);  // every warp is done with buffer b
+        const int b = NB == 2 ? (k & 1) : 0;
+        if (k >= NB) mbar_wait_sleep(&ctl->empty[b], NB == 2 ? (((k >> 1) - 1) & 1) : ((k - 1) & 1));  // every warp is done with buffer b
         const int tile = next < p.N ? next : -1;
         ctl->tile[b] = tile;
         ctl->lownext[b] = 0u;
@@ -657,9 +658,10 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   const long long tpx = (long long)T_h * T_w;
 
   for (int k = 0;; k++) {
-    const int b = k & 1;
-    mbar_wait(&ctl->full[b], (k >> 1) & 1);  // tile id published, views (if any) landed
-    const int n = ctl->tile[b];
+    const int b = k & 1;                          // slot of the per-tile scratch (max, queue)
+    const int sb = NB == 2 ? b : 0;           // staging buffer
+    mbar_wait(&ctl->full[sb], NB == 2 ? ((k >> 1) & 1) : (k & 1));  // tile id published, views (if any) landed
+    const int n = ctl->tile[sb];
     if (n < 0) break;
     const TilePresence tp = pisto_tile_presence(p, n);
     const bool multi = tp.single < 0;
@@ -669,7 +671,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     for (int v = 0; v < V; v++) {
       const ViewDev& vw = p.view[v];
       const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
-      vb[v] = smem_u32(vsm + b * g.buf_floats + g.view_off[v]) + sh;
+      vb[v] = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
     }
     // classes in play, lowest index first
     int cls[C], P = 0;
@@ -696,6 +698,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
     bar_sync(1, ncomp);  // difference maps + max visible; every thread has left the previous tile
+    if (NB == 1 && (tid & 31) == 0) mbar_arrive(&ctl->empty[0]);  // single staging buffer: the raw views are not read again
     if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone; its slot is next pushed to after the next bar_sync
 
     bool exact_all = false;
@@ -711,7 +714,16 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       if (!exact_all && worker && ys < ye) {
         if (P == 2) filter_rows<C, G, F, NP, 1, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (P == 3) filter_rows<C, G, F, NP, 2, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-        else if (C >= 4 && P == 4) filter_rows<C, G, F, NP, (C >= 4 ? 3 : 1), LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        else if (C >= 4 && P == 4) {
+          // three difference fields for four columns do not fit the register file: two passes of two columns each
+          constexpr int K3 = C >= 4 ? 3 : 1;
+          if (NP == 2) {
+            filter_rows<C, G, F, 1, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+            filter_rows<C, G, F, 1, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t + 16u, colB_t + 16u, ymap_s, lab_s, n, x + 2, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          } else {
+            filter_rows<C, G, F, NP, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          }
+        }
       }
       bar_sync(1, ncomp);  // every strip done: the queue is complete
       if (tid == 0) ctl->maxbits[b] = 0u;  // read by everyone before this barrier; next written two tiles from now
@@ -732,13 +744,22 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
           const ViewDev& vw = p.view[v];
           const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, vw.same_h);
           const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, vw.same_w);
-          const uint32_t r0 = vb[v] + g.vbase[v] + Ly.i0 * g.vrow[v], r1 = vb[v] + g.vbase[v] + Ly.i1 * g.vrow[v];
-          const uint32_t c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+          const int r0 = g.vbase[v] + Ly.i0 * g.vrow[v], r1 = g.vbase[v] + Ly.i1 * g.vrow[v];
+          const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+          const float* gsrc = vw.logits + (long long)n * vw.tile_stride;   // single staging buffer: already refilled, read L2 / HBM
 #pragma unroll
           for (int c = 0; c < C; c++) {
-            const uint32_t pl = c * g.plane_bytes[v];
-            const float h0 = __fmaf_rn(Lx.l0, lds_f32(r0 + pl + c0), __fmul_rn(Lx.l1, lds_f32(r0 + pl + c1)));
-            const float h1 = __fmaf_rn(Lx.l0, lds_f32(r1 + pl + c0), __fmul_rn(Lx.l1, lds_f32(r1 + pl + c1)));
+            const int pl = c * g.plane_bytes[v];
+            float x00, x01, x10, x11;
+            if (NB == 2) {
+              x00 = lds_f32(vb[v] + r0 + pl + c0); x01 = lds_f32(vb[v] + r0 + pl + c1);
+              x10 = lds_f32(vb[v] + r1 + pl + c0); x11 = lds_f32(vb[v] + r1 + pl + c1);
+            } else {
+              x00 = __ldg(gsrc + ((r0 + pl + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + pl + c1) >> 2));
+              x10 = __ldg(gsrc + ((r1 + pl + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + pl + c1) >> 2));
+            }
+            const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+            const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
             const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
             a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
           }
@@ -819,7 +840,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
         if (has_label) p.label_out[base + i] = (uint8_t)o;
       }
     }
-    if (need_low) export_rows(n, b, vb);  // whatever the export warps have not got to yet
+    if (need_low) export_rows(n, sb, vb);  // whatever the export warps have not got to yet
     if (do_conf) {
       // every lane of every compute warp reaches this point: full-mask warp reductions are safe
 #pragma unroll
@@ -830,7 +851,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       }
     }
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&ctl->empty[b]);  // this warp is done with staging buffer b
+    if (NB == 2 && (tid & 31) == 0) mbar_arrive(&ctl->empty[sb]);  // this warp is done with staging buffer sb
   }
   if (do_conf) {
     bar_sync(1, ncomp);
@@ -842,8 +863,10 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, FilterGeom* g) {
+static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, int nbuf, FilterGeom* g) {
   memset(g, 0, sizeof(*g));
+  g->nbuf = nbuf;
+  if (nbuf == 1 && p.lowres_out && p.low_fh > 0) return false;  // the export reads the staged views for the whole tile
   if (p.T_w % (2 * NP)) return false;
   const int GX = p.T_w / (2 * NP);
   if (GX > kFMaxThreads - 32 - 32 * kFAux) return false;  // one producer warp, kFAux export warps
@@ -935,16 +958,16 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   g->lab_off = off;
   if (lsm) { off += p.T_h * p.T_w; off = (off + 15) & ~15; }
   off = (off + 127) & ~127;
-  g->views_off = off; off += 2 * 4 * fl;
+  g->views_off = off; off += nbuf * 4 * fl;
   g->smem_bytes = off;
   return off <= h->smem_optin - 1024;
 }
 
-template <int C, int V, int G, int F, int NP, bool LSM>
+template <int C, int V, int G, int F, int NP, bool LSM, int NB>
 int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   FilterGeom g;
-  if (!make_filter_geom(h, p, NP, G, LSM, &g)) return PISTO_OK;  // not launched: caller falls back
-  auto kern = fuse_filter_kernel<C, V, G, F, NP, LSM>;
+  if (!make_filter_geom(h, p, NP, G, LSM, NB, &g)) return PISTO_OK;  // not launched: caller falls back
+  auto kern = fuse_filter_kernel<C, V, G, F, NP, LSM, NB>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
@@ -980,11 +1003,15 @@ static inline int pisto_filter_groups(const FuseParams& p) {
 template <int C, int V, int G, int F>
 static int pisto_launch_filter_f(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   if (np == 2) {
-    const int rc = launch_filter<C, V, G, F, 2, true>(h, p, st, launched);
+    int rc = launch_filter<C, V, G, F, 2, true, 2>(h, p, st, launched);
     if (rc != PISTO_OK || *launched) return rc;
-    return launch_filter<C, V, G, F, 2, false>(h, p, st, launched);
+    if constexpr ((F & 8) == 0) {  // label tile + ONE staging buffer (never with the 32x32 export, which reads the views all tile long)
+      rc = launch_filter<C, V, G, F, 2, true, 1>(h, p, st, launched);
+      if (rc != PISTO_OK || *launched) return rc;
+    }
+    return launch_filter<C, V, G, F, 2, false, 2>(h, p, st, launched);
   }
-  return launch_filter<C, V, G, -1, 1, false>(h, p, st, launched);
+  return launch_filter<C, V, G, -1, 1, false, 2>(h, p, st, launched);
 }
 
 template <int C, int V, int G>
