@@ -88,6 +88,15 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
       return PISTO_ERR_UNSUPPORTED;
     }
   }
+  if (!launched && (a->impl == 0 || a->impl == 5)) {  // large tiles: the same filter on output blocks
+    rc = pisto_launch_fuse_band(h, p, st, &launched);
+    if (rc != PISTO_OK) return rc;
+    if (!launched && a->impl == 5) {
+      pisto_set_error("pisto_fuse_argmax_confusion: impl=5 (block-tiled filtered kernel) has no instantiation for C=%d V=%d T=%dx%d with these options",
+                      p.C, p.V, p.T_h, p.T_w);
+      return PISTO_ERR_UNSUPPORTED;
+    }
+  }
   if (!launched && a->impl != 1) {
     rc = pisto_launch_fuse_stream(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;

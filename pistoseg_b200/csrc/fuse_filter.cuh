@@ -43,11 +43,12 @@ constexpr int kFMaxThreads = PISTO_FTHREADS;
 #endif
 constexpr int kFAux = PISTO_FAUX;  // warps that evaluate the 32x32 logit export concurrently with the row loop
 constexpr int kFQueueCap = 1024;
-constexpr int kFMaxGroups = 4;
+constexpr int kFMaxGroups = 5;
 
 struct FilterGeom {
   int GX, S, threads, cwarps;          // threads per output row, strips, CTA size (incl. the producer warp), compute warps
   int GXP;                             // column pairs per row (T_w / 2)
+  int lab_stride;                      // bytes between rows of the shared-memory label tile
   int strip_y0[33];
   int view_off[PISTO_MAX_VIEWS];       // float offset of each view inside one staging buffer (16-byte aligned)
   int plane_bytes[PISTO_MAX_VIEWS];    // h*w*4
@@ -223,6 +224,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   const bool do_conf = RT ? (p.conf != nullptr && p.gt != nullptr) : ((F & 2) != 0);
   const bool has_label = RT ? (p.label_out != nullptr) : ((F & 16) != 0);
   const int T_w = p.T_w;
+  const int lab_stride = g.lab_stride;
   const uint32_t colg = 16u * g.GXP;
   unsigned int c4[4];
 #pragma unroll
@@ -269,7 +271,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   rebase();
 
   uint32_t rt = rowtab_s + RS * ys, ro_a = rowoff_s + 8u * G * ys;
-  uint32_t lab_a = lab_s + ys * T_w + x;
+  uint32_t lab_a = lab_s + ys * lab_stride + x;
   // direct mode: byte masks are fetched 4 rows ahead of their use (rows past the strip are clamped, never out of bounds)
   constexpr int PD = 4;
   const long long tbase = (long long)n * p.T_h * T_w + x;
@@ -290,18 +292,13 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
 
   // row-table entry: vertical weights (-l0, duplicated for the packed fma) + "source rows moved" flags
   auto load_rowtab = [&](uint32_t a, u64 (&w)[G], unsigned int& flags) {
-    const ulonglong2 t0 = lds_u64x2(a);
-    if (G == 1) { w[0] = t0.x; flags = (unsigned int)t0.y; }
-    else {
-      w[0] = t0.x; w[G > 1 ? 1 : 0] = t0.y;
-      const ulonglong2 t1 = lds_u64x2(a + 16u);
-      if (G == 2) flags = (unsigned int)t1.x;
-      else {
-        w[G > 2 ? 2 : 0] = t1.x;
-        if (G == 3) flags = (unsigned int)t1.y;
-        else { const ulonglong2 t2 = lds_u64x2(a + 32u); w[G - 1] = t2.x; flags = (unsigned int)t2.y; }
-      }
-    }
+    constexpr int CH = (G + 2) / 2;  // 16-byte chunks: G weight slots + one flag slot
+    u64 sl[2 * CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) { const ulonglong2 t = lds_u64x2(a + 16u * c); sl[2 * c] = t.x; sl[2 * c + 1] = t.y; }
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) w[gi] = sl[gi];
+    flags = (unsigned int)sl[G];
   };
 #pragma unroll 1
   for (int yl = ys; yl < ye; yl++) {
@@ -352,7 +349,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
     }
     if (LSM) {
       sts_px<NP>(lab_a, lab4);
-      lab_a += T_w;
+      lab_a += lab_stride;
     } else {
       if (do_conf) {
         if (NP == 2 && unc == 0) count_word<C>(cnt_lo, cnt_hi, gt4, lab4);
@@ -874,7 +871,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   if (S > p.T_h) S = p.T_h;
   if (S > 32) S = 32;
   // scale groups: views with the same de-augmented size share their interpolation weights
-  int G = 0, nmax = 0, cnt[kFMaxGroups] = {0, 0, 0, 0};
+  int G = 0, nmax = 0, cnt[kFMaxGroups] = {0};
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
     if (vw.map.ho >= p.T_h) return false;  // same-size / down-sampling rows: the source-row pair does not move by exactly one
@@ -918,7 +915,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
       if ((p.T_h / period) % s == 0) best = s;
     if (best * 2 > S) S = best;
   }
-  g->GX = GX; g->S = S; g->GXP = p.T_w / 2;
+  g->GX = GX; g->S = S; g->GXP = p.T_w / 2; g->lab_stride = p.T_w;
   g->cwarps = (GX * S + 31) / 32;
   g->threads = g->cwarps * 32 + 32 * kFAux + 32;
   int rps = 0;

@@ -152,3 +152,34 @@ def test_auto_dispatch_uses_the_filter_kernel_and_odd_shapes_fall_back(cuda):
     out = ops.fuse_argmax_confusion([v.to(cuda) for v in views], [0, 0, 0], (224, 224), decide=DECIDE_RAW)
     ref = ops.fuse_argmax_confusion([v.to(cuda) for v in views], [0, 0, 0], (224, 224), decide=DECIDE_RAW, impl=IMPL_GENERIC)
     assert torch.equal(out["labels"], ref["labels"])
+
+
+@pytest.mark.parametrize("T,C,scales", [(512, 4, (1, 1.25, 1.5, 1.75, 2)), (448, 3, (1, 1.25, 1.5, 1.75, 2)), (1024, 4, (1, 1.25, 1.5, 1.75, 2)),
+                                        (512, 4, (0.75, 1.0, 1.25))])
+def test_band_kernel_large_tiles(cuda, T, C, scales):
+    """BASELINE config 5: the block-tiled filtered kernel == the generic kernel on labels and confusion, incl. a presence
+    vector, exact ties, a NaN and a huge-magnitude tile."""
+    from pistoseg_b200._lib import IMPL_BAND
+    N = 3 if T <= 512 else 2
+    cfg = synthetic.cfg5(N=N, T=T, C=C, scales=scales)
+    cfg["views"] = [v.clone() for v in cfg["views"]]
+    cfg["views"][0][0] = torch.round(cfg["views"][0][0])          # coarse values: ties between classes
+    cfg["views"][1][0] = torch.round(cfg["views"][1][0])
+    cfg["views"][2][1, 1, 5, 7] = float("nan")
+    if N > 2:
+        cfg["views"][3][2] *= 1e15
+    for decide in (DECIDE_RAW, DECIDE_SOFTMAX):
+        out = run(cfg, cuda, IMPL_BAND, decide=decide)
+        ref = run(cfg, cuda, IMPL_GENERIC, decide=decide)
+        assert torch.equal(out["labels"], ref["labels"]), (T, decide)
+        assert torch.equal(out["conf"], ref["conf"])
+    present = synthetic.make_present(N, C, 3, single_frac=0.34)
+    bg = (cfg["gt"] == C).to(torch.uint8)
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=C)
+    views = [v.to(cuda) for v in cfg["views"]]
+    a = ops.fuse_argmax_confusion(views, cfg["codes"], (T, T), impl=IMPL_BAND, present=present, bg=bg, **kw)
+    b = ops.fuse_argmax_confusion(views, cfg["codes"], (T, T), impl=IMPL_GENERIC, present=present, bg=bg, **kw)
+    assert torch.equal(a["labels"], b["labels"])
+    # automatic dispatch picks it for these shapes
+    c = ops.fuse_argmax_confusion(views, cfg["codes"], (T, T), present=present, bg=bg, **kw)
+    assert torch.equal(c["labels"], b["labels"])
