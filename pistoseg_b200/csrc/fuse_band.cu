@@ -143,33 +143,65 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
         const int ie = pisto_src_index(g.g_scale_h[gi], y1 - 1, g.g_ho[gi], false).i1;
         const int je = pisto_src_index(g.g_scale_w[gi], x0 + BW - 1, g.g_wo[gi], g.g_same_w[gi]).i1;
         const int nr = ie - ib[gi] + 1, nc = je - jb[gi] + 1, cells = nr * nc, cap = bg.ncols_cap[gi];
+        const unsigned int inv = (unsigned int)((0x100000000ull + nc - 1) / nc);  // idx / nc == umulhi(idx, inv) for idx < 2^16
         const uint32_t ym = ymap_s + g.g_ybytes[gi];
-        for (int idx = tid; idx < cells; idx += nt) {
-          const int di = idx / nc, dj = idx - di * nc;
-          const int i = ib[gi] + di, j = jb[gi] + dj;
-          float y[C - 1];
-          bool first = true;
+        if (V == 2 * G) {
+          // views (2g, 2g+1) form group g (a scale and its flipped twin): both are read in one sweep, all loads of a cell
+          // (2 views x P classes) are independent and two cells are in flight per thread
+          const int va = 2 * gi < V ? 2 * gi : 0, vc = 2 * gi + 1 < V ? 2 * gi + 1 : 0;
+          const float* sa = p.view[va].logits + (long long)n * p.view[va].tile_stride;
+          const float* sc = p.view[vc].logits + (long long)n * p.view[vc].tile_stride;
+          const int ra = g.vrow[va], ca = g.vcol[va], rc = g.vrow[vc], cc = g.vcol[vc];
+          const int basea = g.vbase[va] + cls[0] * g.plane_bytes[va] + ib[gi] * ra + jb[gi] * ca;
+          const int basec = g.vbase[vc] + cls[0] * g.plane_bytes[vc] + ib[gi] * rc + jb[gi] * cc;
+          int dqa[C - 1], dqc[C - 1];
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            if (g.group_of[v] != gi) continue;
-            const float* src = p.view[v].logits + (long long)n * p.view[v].tile_stride;
-            const int a = g.vbase[v] + i * g.vrow[v] + j * g.vcol[v];
-            const float x0v = __ldg(src + ((a + cls[0] * g.plane_bytes[v]) >> 2));
-            mxf = max_nan(mxf, fabsf(x0v));
+          for (int q = 0; q < C - 1; q++) { dqa[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[va]; dqc[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[vc]; }
+#pragma unroll 2
+          for (int idx = tid; idx < cells; idx += nt) {
+            const int di = (int)__umulhi((unsigned)idx, inv), dj = idx - di * nc;
+            const int oa = basea + di * ra + dj * ca, oc = basec + di * rc + dj * cc;
+            const float x0a = __ldg(sa + (oa >> 2)), x0c = __ldg(sc + (oc >> 2));
+            float xa[C - 1], xc[C - 1];
 #pragma unroll
-            for (int q = 0; q < C - 1; q++) {
+            for (int q = 0; q < C - 1; q++)
+              if (q + 1 < P) { xa[q] = __ldg(sa + ((oa + dqa[q]) >> 2)); xc[q] = __ldg(sc + ((oc + dqc[q]) >> 2)); }
+            mxf = max_nan(max_nan(mxf, fabsf(x0a)), fabsf(x0c));
+#pragma unroll
+            for (int q = 0; q < C - 1; q++)
               if (q + 1 < P) {
-                const float xq = __ldg(src + ((a + cls[q + 1] * g.plane_bytes[v]) >> 2));
-                mxf = max_nan(mxf, fabsf(xq));
-                const float t = __fsub_rn(xq, x0v);
-                y[q] = first ? t : __fadd_rn(y[q], t);
+                mxf = max_nan(max_nan(mxf, fabsf(xa[q])), fabsf(xc[q]));
+                sts_f32(ym + q * g.g_mapbytes[gi] + 4u * (di * cap + dj), __fadd_rn(__fsub_rn(xa[q], x0a), __fsub_rn(xc[q], x0c)));
               }
-            }
-            first = false;
           }
+        } else {
+          for (int idx = tid; idx < cells; idx += nt) {
+            const int di = (int)__umulhi((unsigned)idx, inv), dj = idx - di * nc;
+            const int i = ib[gi] + di, j = jb[gi] + dj;
+            float y[C - 1];
+            bool first = true;
 #pragma unroll
-          for (int q = 0; q < C - 1; q++)
-            if (q + 1 < P) sts_f32(ym + q * g.g_mapbytes[gi] + 4u * (di * cap + dj), y[q]);
+            for (int v = 0; v < V; v++) {
+              if (g.group_of[v] != gi) continue;
+              const float* src = p.view[v].logits + (long long)n * p.view[v].tile_stride;
+              const int a = g.vbase[v] + i * g.vrow[v] + j * g.vcol[v];
+              const float x0v = __ldg(src + ((a + cls[0] * g.plane_bytes[v]) >> 2));
+              mxf = max_nan(mxf, fabsf(x0v));
+#pragma unroll
+              for (int q = 0; q < C - 1; q++) {
+                if (q + 1 < P) {
+                  const float xq = __ldg(src + ((a + cls[q + 1] * g.plane_bytes[v]) >> 2));
+                  mxf = max_nan(mxf, fabsf(xq));
+                  const float t = __fsub_rn(xq, x0v);
+                  y[q] = first ? t : __fadd_rn(y[q], t);
+                }
+              }
+              first = false;
+            }
+#pragma unroll
+            for (int q = 0; q < C - 1; q++)
+              if (q + 1 < P) sts_f32(ym + q * g.g_mapbytes[gi] + 4u * (di * cap + dj), y[q]);
+          }
         }
       }
       const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
@@ -212,46 +244,69 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
     }
     if (tid == 0) { ctl->maxbits[0] = 0u; ctl->qcount[0] = 0u; }
     // ---- vector pass: confusion, background overwrite, 16-byte stores ------------------------------------------------------
+    // Two 16-byte vectors (32 pixels) per step; the confusion counts come from bit planes as in confusion.cu (labels and
+    // ground truth are transposed with one shift + one LOP3 per word and plane, then popc(G_a & P_b) per bin), so the cost does
+    // not depend on how ragged the label map is.
     {
       const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
       const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
-      const int vpr = BW / 16, nvec = rows * vpr;  // vectors per block row
-      int pend = 0;
-      for (int i = tid; i < nvec; i += nt) {
-        const int ry = i / vpr, vx = i - ry * vpr;
-        const long long pix = ((long long)n * T_h + y0 + ry) * T_w + x0 + 16 * vx;
-        uint4 lv = make_uint4(labc, labc, labc, labc);
-        if (multi) { const int4 t = lds_i4(lab_s + ry * BW + 16 * vx); lv = make_uint4(t.x, t.y, t.z, t.w); }
-        const unsigned int lw[4] = {lv.x, lv.y, lv.z, lv.w};
-        if (do_conf) {
-          const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.gt + pix));
-          const unsigned int gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      const int vpr = BW / 32, ngrp = rows * vpr;  // 32-pixel groups per block row
+      unsigned int cnt[BINS];
 #pragma unroll
-          for (int q = 0; q < 4; q++) count_word<C>(cnt_lo, cnt_hi, gw[q], lw[q]);
-          pend += 16;
+      for (int i = 0; i < BINS; i++) cnt[i] = 0;
+      for (int i = tid; i < ngrp; i += nt) {
+        const int ry = i / vpr, vx = i - ry * vpr;
+        const long long pix = ((long long)n * T_h + y0 + ry) * T_w + x0 + 32 * vx;
+        unsigned int lw[8];
+        if (multi) {
+          const int4 t0 = lds_i4(lab_s + ry * BW + 32 * vx), t1 = lds_i4(lab_s + ry * BW + 32 * vx + 16);
+          lw[0] = t0.x; lw[1] = t0.y; lw[2] = t0.z; lw[3] = t0.w; lw[4] = t1.x; lw[5] = t1.y; lw[6] = t1.z; lw[7] = t1.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; q++) lw[q] = labc;
+        }
+        if (do_conf) {
+          const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(p.gt + pix)), g1 = __ldg(reinterpret_cast<const uint4*>(p.gt + pix + 16));
+          const unsigned int gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          unsigned int gp0 = 0, gp1 = 0, gpx = 0, lp0 = 0, lp1 = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const unsigned int m = 0x01010101u << j;
+            gp0 |= (gw[j] << j) & m;
+            gp1 |= (j == 0 ? (gw[j] >> 1) : (gw[j] << (j - 1))) & m;
+            const unsigned int hi = ((gw[j] >> 2) & 0x3f3f3f3fu) + 0x3f3f3f3fu;  // bit 6 set iff the byte is >= 4
+            gpx |= (j <= 6 ? (hi >> (6 - j)) : (hi << (j - 6))) & m;
+            lp0 |= (lw[j] << j) & m;                                             // labels are < C <= 4: two planes
+            lp1 |= (j == 0 ? (lw[j] >> 1) : (lw[j] << (j - 1))) & m;
+          }
+          unsigned int Gm[4], Pm[4];
+          Gm[0] = ~gp1 & ~gp0 & ~gpx; Gm[1] = ~gp1 & gp0 & ~gpx; Gm[2] = gp1 & ~gp0 & ~gpx; Gm[3] = gp1 & gp0 & ~gpx;
+          Pm[0] = ~lp1 & ~lp0; Pm[1] = ~lp1 & lp0; Pm[2] = lp1 & ~lp0; Pm[3] = lp1 & lp0;
+#pragma unroll
+          for (int a = 0; a < C; a++)
+#pragma unroll
+            for (int c = 0; c < C; c++) cnt[a * C + c] += __popc(Gm[a < 4 ? a : 0] & Pm[c < 4 ? c : 0]);
         }
         if (has_label) {
-          uint4 o = lv;
-          if (has_bg) {
-            const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bg + pix));
-            const unsigned int bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            unsigned int ow[4];
+          unsigned int ow[8];
 #pragma unroll
-            for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
-            o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          for (int q = 0; q < 8; q++) ow[q] = lw[q];
+          if (has_bg) {
+            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(p.bg + pix)), b1 = __ldg(reinterpret_cast<const uint4*>(p.bg + pix + 16));
+            const unsigned int bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
           }
-          *reinterpret_cast<uint4*>(p.label_out + pix) = o;
+          reinterpret_cast<uint4*>(p.label_out + pix)[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          reinterpret_cast<uint4*>(p.label_out + pix)[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
         }
       }
-      if (do_conf) {  // flush the packed 8-bit counters after every block (at most 16 * ceil(nvec / nt) <= 255 pixels per thread)
-        (void)pend;
+      if (do_conf) {
 #pragma unroll
         for (int bn = 0; bn < BINS; bn++) {
-          unsigned int cv = (unsigned int)(((bn < 8 ? cnt_lo : cnt_hi) >> (8 * (bn & 7))) & 0xffull);
-          cv = __reduce_add_sync(0xffffffffu, cv);
+          const unsigned int cv = __reduce_add_sync(0xffffffffu, cnt[bn]);
           if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
         }
-        cnt_lo = cnt_hi = 0;
       }
     }
     __syncthreads();  // tables / label tile / queue are reused by the next item
@@ -291,19 +346,18 @@ int launch_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launch
     g.vcol[v] = 4 * (vw.map.aj * vw.w + vw.map.bj);
   }
   if (Gn != G) return PISTO_OK;
-  // block shape: 512 columns (4 per thread, 128 threads per row), 3 strips of 16 rows
+  // block shape: 512 columns (4 per thread, 128 threads per row), 3 strips of 24 rows
   b.BW = p.T_w < 512 ? p.T_w : 512;
-  if (p.T_w % b.BW || b.BW % 16) return PISTO_OK;
+  if (p.T_w % b.BW || b.BW % 32) return PISTO_OK;
   b.GX = b.BW / 4;
   b.S = (kBThreads / b.GX) < 8 ? (kBThreads / b.GX) : 8;
   if (b.S < 1) return PISTO_OK;
-  const int rps = 16;
+  const int rps = 24;
   b.BH = b.S * rps;
   if (b.BH > p.T_h) { b.BH = p.T_h; }
   for (int q = 0; q <= b.S; q++) b.strip_y0[q] = q * rps < b.BH ? q * rps : b.BH;
   b.nby = (p.T_h + b.BH - 1) / b.BH;
   b.nbx = p.T_w / b.BW;
-  if (16 * ((b.BH * (b.BW / 16) + kBThreads - 1) / kBThreads) > 255) return PISTO_OK;  // packed 8-bit confusion counters
   // capacity of every group's sub-rectangle
   for (int gi = 0; gi < G; gi++) {
     int nr = 0, nc = 0;
@@ -372,7 +426,7 @@ int pisto_launch_fuse_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, b
   if (p.dec.mask_mode == PISTO_MASK_MULTIPLY) return PISTO_OK;
   if (!p.label_out && !(p.conf && p.gt)) return PISTO_OK;
   if (p.conf && p.gt && p.C > 4) return PISTO_OK;
-  if (p.T_h > 65535 || p.T_w > 65535 || p.T_w % 16) return PISTO_OK;
+  if (p.T_h > 65535 || p.T_w > 65535 || p.T_w % 32) return PISTO_OK;
   if (((uintptr_t)p.label_out | (uintptr_t)p.bg | (uintptr_t)p.gt) & 15) return PISTO_OK;
   if (((long long)p.T_h * p.T_w) % 16) return PISTO_OK;
   for (int v = 0; v < p.V; v++)

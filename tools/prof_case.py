@@ -12,7 +12,8 @@ kw2 = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, l
 cfg, kw = {"cfg2": (lambda: synthetic.cfg2(N=1024), kw2), "cfg2multi": (lambda: synthetic.cfg2(N=1024, single_frac=0.0), kw2),
            "cfg2single": (lambda: synthetic.cfg2(N=1024, single_frac=1.0), kw2),
            "cfg1": (lambda: synthetic.cfg1(N=1024), dict(decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)),
-           "cfg3": (lambda: synthetic.cfg3(N=1000), dict(decide=DECIDE_SOFTMAX))}[name]
+           "cfg3": (lambda: synthetic.cfg3(N=1000), dict(decide=DECIDE_SOFTMAX)),
+           "cfg5": (lambda: synthetic.cfg5(N=8, T=512), dict(decide=DECIDE_SOFTMAX))}[name]
 cfg = cfg()
 
 
@@ -25,6 +26,6 @@ views = [rep(v, N) for v in cfg["views"]]
 args = {k: (rep(cfg[k], N) if cfg.get(k) is not None else None) for k in ("present", "bg", "gt")}
 conf = ops.new_confusion(cfg["C"], dev) if args["gt"] is not None else None
 for _ in range(4):
-    ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), conf=conf, impl=impl, **args, **kw)
+    ops.fuse_argmax_confusion(views, cfg["codes"], (cfg["T"], cfg["T"]), conf=conf, impl=impl, **args, **kw)
 torch.cuda.synchronize()
 print("ok")
