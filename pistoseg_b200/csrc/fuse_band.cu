@@ -268,24 +268,7 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
         if (do_conf) {
           const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(p.gt + pix)), g1 = __ldg(reinterpret_cast<const uint4*>(p.gt + pix + 16));
           const unsigned int gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          unsigned int gp0 = 0, gp1 = 0, gpx = 0, lp0 = 0, lp1 = 0;
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const unsigned int m = 0x01010101u << j;
-            gp0 |= (gw[j] << j) & m;
-            gp1 |= (j == 0 ? (gw[j] >> 1) : (gw[j] << (j - 1))) & m;
-            const unsigned int hi = ((gw[j] >> 2) & 0x3f3f3f3fu) + 0x3f3f3f3fu;  // bit 6 set iff the byte is >= 4
-            gpx |= (j <= 6 ? (hi >> (6 - j)) : (hi << (j - 6))) & m;
-            lp0 |= (lw[j] << j) & m;                                             // labels are < C <= 4: two planes
-            lp1 |= (j == 0 ? (lw[j] >> 1) : (lw[j] << (j - 1))) & m;
-          }
-          unsigned int Gm[4], Pm[4];
-          Gm[0] = ~gp1 & ~gp0 & ~gpx; Gm[1] = ~gp1 & gp0 & ~gpx; Gm[2] = gp1 & ~gp0 & ~gpx; Gm[3] = gp1 & gp0 & ~gpx;
-          Pm[0] = ~lp1 & ~lp0; Pm[1] = ~lp1 & lp0; Pm[2] = lp1 & ~lp0; Pm[3] = lp1 & lp0;
-#pragma unroll
-          for (int a = 0; a < C; a++)
-#pragma unroll
-            for (int c = 0; c < C; c++) cnt[a * C + c] += __popc(Gm[a < 4 ? a : 0] & Pm[c < 4 ? c : 0]);
+          bitslice_count<C>(gw, lw, cnt);
         }
         if (has_label) {
           unsigned int ow[8];

@@ -210,6 +210,32 @@ __device__ __forceinline__ void count_word(u64& lo, u64& hi, unsigned int g4, un
   }
 }
 
+// Confusion counts of 32 pixels from bit planes (the method of confusion.cu): word j of gw / lw contributes bit k of its bytes
+// at bit j of the plane byte -- one shift and one LOP3 per (word, plane), the pixel permutation is the same for every plane --
+// then cnt[a*C + b] += popc(G_a & L_b).  Labels are < C <= 4 (two planes); ground-truth bytes >= 4 are never counted.  The
+// cost does not depend on how ragged the label map is.
+template <int C>
+__device__ __forceinline__ void bitslice_count(const unsigned int (&gw)[8], const unsigned int (&lw)[8], unsigned int (&cnt)[C * C]) {
+  unsigned int gp0 = 0, gp1 = 0, gpx = 0, lp0 = 0, lp1 = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const unsigned int m = 0x01010101u << j;
+    gp0 |= (gw[j] << j) & m;
+    gp1 |= (j == 0 ? (gw[j] >> 1) : (gw[j] << (j - 1))) & m;
+    const unsigned int hi = ((gw[j] >> 2) & 0x3f3f3f3fu) + 0x3f3f3f3fu;  // bit 6 set iff the byte is >= 4
+    gpx |= (j <= 6 ? (hi >> (6 - j)) : (hi << (j - 6))) & m;
+    lp0 |= (lw[j] << j) & m;
+    lp1 |= (j == 0 ? (lw[j] >> 1) : (lw[j] << (j - 1))) & m;
+  }
+  unsigned int Gm[4], Pm[4];
+  Gm[0] = ~gp1 & ~gp0 & ~gpx; Gm[1] = ~gp1 & gp0 & ~gpx; Gm[2] = gp1 & ~gp0 & ~gpx; Gm[3] = gp1 & gp0 & ~gpx;
+  Pm[0] = ~lp1 & ~lp0; Pm[1] = ~lp1 & lp0; Pm[2] = lp1 & ~lp0; Pm[3] = lp1 & lp0;
+#pragma unroll
+  for (int a = 0; a < C; a++)
+#pragma unroll
+    for (int c = 0; c < C; c++) cnt[a * C + c] += __popc(Gm[a < 4 ? a : 0] & Pm[c < 4 ? c : 0]);
+}
+
 // ---- the row loop of one strip, K difference fields ----------------------------------------------------------------
 // LSM: labels go to the shared-memory label tile (background / confusion / the global store happen in the vector pass
 // after the exact pass); otherwise they go straight to global memory with the byte masks prefetched 4 rows ahead.
@@ -784,22 +810,32 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     if (LSM || !multi) {
       const long long base = (long long)n * tpx;
       const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
-      // packed 8-bit confusion counters: at most 255 pixels per thread between flushes
-      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0) &&
-                          (!do_conf || 16 * ((tpx / 16 + nt - 1) / nt) <= 255);
+      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
       const int nvec = vec_ok ? (int)(tpx / 16) : 0;
       const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
       constexpr int UN = 4;  // independent 16-byte loads in flight per thread
+      unsigned int cnt32[BINS];
+#pragma unroll
+      for (int i = 0; i < BINS; i++) cnt32[i] = 0;
       for (int i0 = tid; i0 < nvec; i0 += UN * nt) {
         uint4 bgv[UN], gv[UN], lv[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) {
           const int i = i0 + u * nt;
+          gv[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // out of range: never counted
+          lv[u] = make_uint4(labc, labc, labc, labc);
           if (i < nvec) {
             if (has_bg) bgv[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
             if (do_conf) gv[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
             if (LSM && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
-            else lv[u] = make_uint4(labc, labc, labc, labc);
+          }
+        }
+        if (do_conf) {  // two vectors = 32 pixels per bit-sliced count
+#pragma unroll
+          for (int u = 0; u < UN; u += 2) {
+            const unsigned int gw[8] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w, gv[u + 1].x, gv[u + 1].y, gv[u + 1].z, gv[u + 1].w};
+            const unsigned int lw8[8] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w, lv[u + 1].x, lv[u + 1].y, lv[u + 1].z, lv[u + 1].w};
+            bitslice_count<C>(gw, lw8, cnt32);
           }
         }
 #pragma unroll
@@ -807,11 +843,6 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
           const int i = i0 + u * nt;
           if (i < nvec) {
             const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
-            if (do_conf) {
-              const unsigned int gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-#pragma unroll
-              for (int q = 0; q < 4; q++) count_word<C>(cnt_lo, cnt_hi, gw[q], lw[q]);
-            }
             if (has_label) {
               uint4 o = lv[u];
               if (has_bg) {
@@ -824,6 +855,13 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
               reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
             }
           }
+        }
+      }
+      if (do_conf) {
+#pragma unroll
+        for (int bn = 0; bn < BINS; bn++) {
+          const unsigned int cv = __reduce_add_sync(0xffffffffu, cnt32[bn]);
+          if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
         }
       }
       for (int i = nvec * 16 + tid; i < (int)tpx; i += nt) {  // unaligned / ragged shapes
