@@ -72,5 +72,6 @@ int pisto_launch_fuse_generic(pisto_ctx* h, const FuseParams& p, cudaStream_t st
 int pisto_launch_fuse_stream(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched);
 int pisto_launch_fuse_identity(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
+int pisto_launch_fuse_fullres(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 int pisto_launch_fuse_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 int pisto_launch_fuse_block(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);

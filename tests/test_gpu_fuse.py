@@ -235,3 +235,33 @@ def test_identity_view_fast_path_equals_generic(cuda, C):
                 b = ops.fuse_argmax_confusion([view], [0], (T, T), conf=ops.new_confusion(C, cuda), impl=IMPL_GENERIC, **kw)
                 assert torch.equal(a["labels"], b["labels"]), (C, mask, decide)
                 assert torch.equal(a["conf"], b["conf"]), (C, mask, decide)
+
+
+@pytest.mark.parametrize("T,C", [((224, 224), 3), ((96, 120), 4), ((70, 45), 3)])
+def test_fullres_d4_kernel_equals_generic_and_oracle(cuda, T, C):
+    """ttach d4 on full-resolution logits (the literal infer_pseudo_masks.py path): the streaming full-resolution kernel
+    (automatic dispatch) == the generic kernel == the oracle, for fused scores, labels, 32x32 export and confusion."""
+    from oracle import tta
+    g = torch.Generator().manual_seed(31 + C)
+    N = 5
+    views, codes = [], []
+    for hf, ang in tta.D4_VIEWS:
+        code = tta.deaug_code(hf, ang)
+        shape = (N, C, T[1], T[0]) if code % 2 else (N, C, T[0], T[1])
+        views.append(torch.round(torch.randn(shape, generator=g) * 8) / 8); codes.append(code)
+    present = synthetic.make_present(N, C, 5, single_frac=0.4)
+    gt = torch.randint(0, C + 1, (N,) + T, generator=g, dtype=torch.uint8)
+    bg = (torch.rand((N,) + T, generator=g) < 0.2).to(torch.uint8)
+    vg = [v.to(cuda) for v in views]
+    low = (32, 32) if T == (224, 224) else None
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=present, bg=bg, bg_match=1, bg_label=C, gt=gt, lowres=low, want_fused=True)
+    a = ops.fuse_argmax_confusion(vg, codes, T, conf=ops.new_confusion(C, cuda), **kw)
+    b = ops.fuse_argmax_confusion(vg, codes, T, conf=ops.new_confusion(C, cuda), impl=IMPL_GENERIC, **kw)
+    ref = ofuse.fuse_views(views, codes, T)
+    assert torch.equal(a["fused"].cpu(), ref)
+    for k in ("fused", "labels", "conf") + (("lowres",) if low else ()):
+        assert torch.equal(a[k], b[k]), k
+    # without the score outputs (single-label tiles then skip the views entirely)
+    kw.update(want_fused=False, lowres=None)
+    a2 = ops.fuse_argmax_confusion(vg, codes, T, conf=ops.new_confusion(C, cuda), **kw)
+    assert torch.equal(a2["labels"], b["labels"]) and torch.equal(a2["conf"], b["conf"])
