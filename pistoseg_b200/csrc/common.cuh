@@ -251,3 +251,23 @@ __device__ __forceinline__ void pisto_softmax_inplace(float (&x)[C]) {
 #pragma unroll
   for (int c = 0; c < C; c++) x[c] = __fdiv_rn(x[c], sum);
 }
+
+// Same softmax for the streaming kernels' PROB_MEAN path, where V*C*T^2 exponentials per tile make the MUFU unit the
+// bottleneck: exp as ex2.approx(x * log2 e) (relative error < 4e-7 on the argument range of a max-subtracted softmax) and one
+// reciprocal instead of C divisions.  Probabilities differ from the exact version by < 1e-6 absolute -- inside the 1e-5
+// float gate that applies to PROB_MEAN scores anyway (CUDA expf and the reference's Sleef expf already differ by 1 ulp).
+template <int C>
+__device__ __forceinline__ void pisto_softmax_fast(float (&x)[C]) {
+  float m = x[0];
+#pragma unroll
+  for (int c = 1; c < C; c++) m = fmaxf(m, x[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    x[c] = __expf(__fsub_rn(x[c], m));
+    sum = __fadd_rn(sum, x[c]);
+  }
+  const float r = __frcp_rn(sum);
+#pragma unroll
+  for (int c = 0; c < C; c++) x[c] = __fmul_rn(x[c], r);
+}

@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
             float s0[C], s1[C];
 #pragma unroll
             for (int c = 0; c < C; c++) unpack2(u[c], s0[c], s1[c]);
-            pisto_softmax_inplace<C>(s0);
-            pisto_softmax_inplace<C>(s1);
+            pisto_softmax_fast<C>(s0);
+            pisto_softmax_fast<C>(s1);
 #pragma unroll
             for (int c = 0; c < C; c++) u[c] = pack2(s0[c], s1[c]);
           }
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
               const float h1 = __fmaf_rn(wl0, lds_f32(pl + ro.y + oa), __fmul_rn(wl1, lds_f32(pl + ro.y + ob)));
               u[c] = __fmaf_rn(er.x, h0, __fmul_rn(er.z, h1));
             }
-            if (PROB) pisto_softmax_inplace<C>(u);
+            if (PROB) pisto_softmax_fast<C>(u);
 #pragma unroll
             for (int c = 0; c < C; c++) a[c] = (v == 0) ? u[c] : __fadd_rn(a[c], u[c]);
           }
