@@ -756,50 +756,89 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     if (multi) {
       const unsigned int nq = ctl->qcount[b];
       if (nq > (unsigned)kFQueueCap && !exact_all) { exact_all = true; cnt_lo = cnt_hi = 0; }  // overflow: redo the whole tile
+      // A queued pixel is evaluated by a whole warp: lane l computes the bilinear sample of (view l / C, class l % C), the
+      // sums are then formed in view order through shuffles -- the latency of one pixel is that of one sample, and the few
+      // queued pixels of a tile are spread over all warps.  (The whole-tile fallback keeps one pixel per thread.)
+      const bool warp_coop = !exact_all && V * C <= 32;
       const int nfix = exact_all ? T_h * T_w : (int)nq;
-      for (int j = tid; j < nfix; j += nt) {
+      const int lane = tid & 31;
+      for (int j = warp_coop ? (tid >> 5) : tid; j < nfix; j += warp_coop ? g.cwarps : nt) {
         float a[C];
         int yy, xx;
         if (exact_all) { yy = j / T_w; xx = j - yy * T_w; }
         else { const uint32_t e = queue[j]; yy = (int)(e >> 16); xx = (int)(e & 0xffffu); }
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const ViewDev& vw = p.view[v];
-          const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, vw.same_h);
-          const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, vw.same_w);
-          const int r0 = g.vbase[v] + Ly.i0 * g.vrow[v], r1 = g.vbase[v] + Ly.i1 * g.vrow[v];
-          const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
-          const float* gsrc = vw.logits + (long long)n * vw.tile_stride;   // single staging buffer: already refilled, read L2 / HBM
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            const int pl = c * g.plane_bytes[v];
+        if (warp_coop) {
+          float o = 0.f;
+          if (lane < V * C) {
+            const int v = lane / C, c = lane - v * C;
+            const ViewDev& vw = p.view[v];
+            const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, vw.same_h);
+            const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, vw.same_w);
+            const int pl = g.vbase[v] + c * g.plane_bytes[v];
+            const int r0 = pl + Ly.i0 * g.vrow[v], r1 = pl + Ly.i1 * g.vrow[v];
+            const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
             float x00, x01, x10, x11;
             if (NB == 2) {
-              x00 = lds_f32(vb[v] + r0 + pl + c0); x01 = lds_f32(vb[v] + r0 + pl + c1);
-              x10 = lds_f32(vb[v] + r1 + pl + c0); x11 = lds_f32(vb[v] + r1 + pl + c1);
+              const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+              const uint32_t base = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
+              x00 = lds_f32(base + r0 + c0); x01 = lds_f32(base + r0 + c1); x10 = lds_f32(base + r1 + c0); x11 = lds_f32(base + r1 + c1);
             } else {
-              x00 = __ldg(gsrc + ((r0 + pl + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + pl + c1) >> 2));
-              x10 = __ldg(gsrc + ((r1 + pl + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + pl + c1) >> 2));
+              const float* gsrc = vw.logits + (long long)n * vw.tile_stride;
+              x00 = __ldg(gsrc + ((r0 + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + c1) >> 2));
+              x10 = __ldg(gsrc + ((r1 + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + c1) >> 2));
             }
             const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
             const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
-            const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
-            a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+            o = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            a[c] = __shfl_sync(0xffffffffu, o, c);
+#pragma unroll
+            for (int v = 1; v < V; v++) a[c] = __fadd_rn(a[c], __shfl_sync(0xffffffffu, o, (v * C + c) & 31));
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const ViewDev& vw = p.view[v];
+            const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, vw.same_h);
+            const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, vw.same_w);
+            const int r0 = g.vbase[v] + Ly.i0 * g.vrow[v], r1 = g.vbase[v] + Ly.i1 * g.vrow[v];
+            const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+            const float* gsrc = vw.logits + (long long)n * vw.tile_stride;   // single staging buffer: already refilled, read L2 / HBM
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              const int pl = c * g.plane_bytes[v];
+              float x00, x01, x10, x11;
+              if (NB == 2) {
+                x00 = lds_f32(vb[v] + r0 + pl + c0); x01 = lds_f32(vb[v] + r0 + pl + c1);
+                x10 = lds_f32(vb[v] + r1 + pl + c0); x11 = lds_f32(vb[v] + r1 + pl + c1);
+              } else {
+                x00 = __ldg(gsrc + ((r0 + pl + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + pl + c1) >> 2));
+                x10 = __ldg(gsrc + ((r1 + pl + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + pl + c1) >> 2));
+              }
+              const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+              const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+              const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+              a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+            }
           }
         }
         const int lab = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
-        if (LSM) {
-          labsm[yy * T_w + xx] = (uint8_t)lab;
-        } else {
-          const long long pix = (long long)n * tpx + yy * T_w + xx;
-          if (do_conf) {
-            const unsigned int gg = p.gt[pix];
-            if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
-          }
-          if (has_label) {
-            unsigned int o = (unsigned)lab;
-            if (has_bg && p.bg[pix] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
-            p.label_out[pix] = (uint8_t)o;
+        if (!warp_coop || lane == 0) {
+          if (LSM) {
+            labsm[yy * T_w + xx] = (uint8_t)lab;
+          } else {
+            const long long pix = (long long)n * tpx + yy * T_w + xx;
+            if (do_conf) {
+              const unsigned int gg = p.gt[pix];
+              if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
+            }
+            if (has_label) {
+              unsigned int o2 = (unsigned)lab;
+              if (has_bg && p.bg[pix] == (uint8_t)p.bg_match) o2 = (unsigned)p.bg_label;
+              p.label_out[pix] = (uint8_t)o2;
+            }
           }
         }
       }
