@@ -752,6 +752,24 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       if (tid == 0) ctl->maxbits[b] = 0u;  // read by everyone before this barrier; next written two tiles from now
     }
 
+    // The byte masks of the vector pass' first batch are requested now, so that their HBM / L2 latency is covered by the exact
+    // pass and its barrier instead of being paid at the start of the vector pass.
+    constexpr int UN = 4;  // independent 16-byte loads in flight per thread
+    const long long vbase_px = (long long)n * tpx;
+    const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
+    const int nvec = (vec_ok && (LSM || !multi)) ? (int)(tpx / 16) : 0;
+    uint4 bgn[UN], gn[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int i = tid + u * nt;
+      gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // out of range: never counted
+      bgn[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < nvec) {
+        if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + vbase_px) + i);
+        if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + vbase_px) + i);
+      }
+    }
+
     // ---- exact pass: queued pixels (or the whole tile), operation by operation as the reference ----------------------
     if (multi) {
       const unsigned int nq = ctl->qcount[b];
@@ -847,12 +865,9 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 
     // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label) -----
     if (LSM || !multi) {
-      const long long base = (long long)n * tpx;
+      const long long base = vbase_px;
       const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
-      const bool vec_ok = (tpx % 16 == 0) && ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
-      const int nvec = vec_ok ? (int)(tpx / 16) : 0;
       const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
-      constexpr int UN = 4;  // independent 16-byte loads in flight per thread
       unsigned int cnt32[BINS];
 #pragma unroll
       for (int i = 0; i < BINS; i++) cnt32[i] = 0;
@@ -861,12 +876,17 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 #pragma unroll
         for (int u = 0; u < UN; u++) {
           const int i = i0 + u * nt;
-          gv[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // out of range: never counted
+          bgv[u] = bgn[u]; gv[u] = gn[u];           // this batch was requested one step ago
           lv[u] = make_uint4(labc, labc, labc, labc);
+          if (i < nvec && LSM && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {              // request the next batch
+          const int i = i0 + (UN + u) * nt;
+          gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
           if (i < nvec) {
-            if (has_bg) bgv[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
-            if (do_conf) gv[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
-            if (LSM && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
+            if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+            if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
           }
         }
         if (do_conf) {  // two vectors = 32 pixels per bit-sliced count
