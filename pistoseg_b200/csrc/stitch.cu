@@ -29,13 +29,43 @@ __global__ void __launch_bounds__(kThreads) stitch_kernel(const float* __restric
     cnt = count[pix];
   }
   const long long tile_elems = (long long)C * th * tw;
+  // Bounding box of the block's pixels (256 consecutive pixels in row-major order: one or two canvas rows).  Each chunk of
+  // tile positions is first filtered against it, cooperatively and ORDER-PRESERVING (ballot + prefix), so that a pixel only
+  // visits the few tiles that can cover it -- still in increasing tile index, i.e. in the reference's summation order.
+  const long long pix_lo = (long long)blockIdx.x * blockDim.x;
+  const long long pix_hi = min(HW, pix_lo + (long long)blockDim.x) - 1;
+  const int by0 = (int)(pix_lo / W), by1 = (int)(pix_hi / W);
+  const int bx0 = by0 == by1 ? (int)(pix_lo - (long long)by0 * W) : 0, bx1 = by0 == by1 ? (int)(pix_hi - (long long)by1 * W) : W - 1;
+  __shared__ int sidx[kPosChunk];      // indices (into the chunk) of the tiles that touch the block, increasing
+  __shared__ int wcount[kThreads / 32 + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int k0 = 0; k0 < n; k0 += kPosChunk) {
     const int kn = min(kPosChunk, n - k0);
     __syncthreads();
     for (int i = threadIdx.x; i < kn; i += blockDim.x) spos[i] = pos[k0 + i];
     __syncthreads();
+    int nhit = 0;
+    for (int base = 0; base < kn; base += blockDim.x) {   // kPosChunk / kThreads rounds
+      const int i = base + threadIdx.x;
+      bool hit = false;
+      if (i < kn) {
+        const pisto_tile_pos_t t = spos[i];
+        hit = t.y <= by1 && t.y + t.crop_h > by0 && t.x <= bx1 && t.x + t.crop_w > bx0;
+      }
+      const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) wcount[wid] = __popc(bal);
+      __syncthreads();
+      int off = nhit;
+      for (int w = 0; w < wid; w++) off += wcount[w];
+      int tot = nhit;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += wcount[w];
+      if (hit) sidx[off + __popc(bal & ((1u << lane) - 1u))] = i;
+      nhit = tot;
+      __syncthreads();
+    }
     if (!live) continue;
-    for (int k = 0; k < kn; k++) {
+    for (int q = 0; q < nhit; q++) {
+      const int k = sidx[q];
       const pisto_tile_pos_t t = spos[k];
       const int dy = Y - t.y, dx = X - t.x;
       if (dy < 0 || dx < 0 || dy >= t.crop_h || dx >= t.crop_w) continue;

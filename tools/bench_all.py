@@ -99,6 +99,36 @@ emit("upsample_bilinear f32 28->224 (C=3)", 8192, "tiles", ms, 3 * 4 * (28 * 28 
 x64 = torch.randn((3, 2000, 2500), device=dev, dtype=torch.float64)
 ms = timeit(lambda: ops.upsample_bilinear(x64, (1600, 2000)), 10)
 emit("upsample_bilinear f64 2000x2500 -> 1600x2000 (C=3)", 1, "images", ms, 3 * 8 * (2000 * 2500 + 1600 * 2000))
+# ---- big-mask stitch (segmentation_test.py:141-215) and OEEM CAM ensemble (prepare_seg_inputs.py:96-138) -------------------
+from pistoseg_b200 import stitch  # noqa: E402
+H_, W_ = 2000, 2500
+scales_ = (0.75, 1.0, 1.25, 1.5, 1.75)
+tiles_, poss_, crops_ = {}, {}, {}
+tile_bytes = 0
+for sc in scales_:
+    hs, ws = int(H_ * sc), int(W_ * sc)
+    ys = list(range(0, max(hs - 224, 0) + 1, 112)); xs = list(range(0, max(ws - 224, 0) + 1, 112))
+    if ys[-1] != hs - 224: ys.append(hs - 224)
+    if xs[-1] != ws - 224: xs.append(ws - 224)
+    pos = [(y, x) for y in ys for x in xs]
+    tiles_[sc] = torch.randn((len(pos), 3, 224, 224), generator=g).to(dev); poss_[sc] = pos; crops_[sc] = [(224, 224)] * len(pos)
+    tile_bytes += tiles_[sc].numel() * 4
+gt_ = torch.randint(0, 4, (H_, W_), generator=g, dtype=torch.uint8).to(dev)
+
+
+def big_mask():
+    f = stitch.BigMaskFuser((H_, W_), 3, dev)
+    for sc in scales_:
+        f.add_tiles(tiles_[sc], sc, poss_[sc], crops_[sc])
+    conf = ops.new_confusion(3, dev)
+    return f.finish(gt=gt_, conf=conf)
+
+
+ms = timeit(big_mask, 3, 1)
+canvas_bytes = sum(int(H_ * sc) * int(W_ * sc) for sc in scales_) * 8 * 4 * 3 + H_ * W_ * 8 * 3 * (2 * len(scales_) + 1)
+emit("big-mask fusion 2000x2500, 5 scales, 50% overlapping 224 tiles: softmax + f64 overlap-add + f64 resize + argmax + confusion", 1, "images", ms,
+     tile_bytes + canvas_bytes, tiles=sum(len(v) for v in poss_.values()))
+del tiles_
 # ---- mosaic ---------------------------------------------------------------------------------------------------------
 rng = np.random.default_rng(0)
 P = 2048
