@@ -147,6 +147,28 @@ def test_stitch_exact_without_softmax(cuda):
     assert np.array_equal(got, ref)
 
 
+def test_stitch_many_tiles_keeps_the_reference_order(cuda):
+    """More tiles than one position chunk (512), heavy overlap, ragged crops, canvas width not a multiple of the block: the
+    float64 sums must equal the reference's sequential `canvas[y:y+h, x:x+w] += tile` loop bit for bit (order matters)."""
+    rng = np.random.default_rng(8)
+    C, side, H, W, n = 3, 24, 211, 309, 1300
+    tiles = (rng.standard_normal((n, C, side, side)) * 1e3).astype(np.float32)   # large dynamic range: order-sensitive sums
+    pos = []
+    ref = np.zeros((C, H, W)); cnt = np.zeros((H, W))
+    for k in range(n):
+        y, x = int(rng.integers(0, H - 1)), int(rng.integers(0, W - 1))
+        ch, cw = int(rng.integers(1, side + 1)), int(rng.integers(1, side + 1))
+        hh, ww = min(ch, H - y), min(cw, W - x)
+        ref[:, y:y + hh, x:x + ww] += tiles[k][:, :hh, :ww].astype(np.float64)
+        cnt[y:y + hh, x:x + ww] += 1
+        pos.append([y, x, ch, cw])
+    canvas = torch.zeros((C, H, W), dtype=torch.float64, device=cuda)
+    count = torch.zeros((H, W), dtype=torch.float64, device=cuda)
+    ops.stitch_accumulate(torch.from_numpy(tiles).to(cuda), pos, canvas, count, softmax=False)
+    assert np.array_equal(canvas.cpu().numpy(), ref)
+    assert np.array_equal(count.cpu().numpy(), cnt)
+
+
 def test_argmax_f64_present_mask(cuda):
     g = torch.Generator().manual_seed(51)
     e = torch.randn((4, 50, 60), generator=g, dtype=torch.float64)
