@@ -661,7 +661,9 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
         const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
         vb[v] = smem_u32(vsm + b * g.buf_floats + g.view_off[v]) + sh;
       }
+#ifndef PISTO_X_SKIP_EXPORT
       export_rows(n, b, vb);
+#endif
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&ctl->empty[b]);
     }
@@ -712,7 +714,11 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     u64 cnt_lo = 0, cnt_hi = 0;
 
     // ---- pre-pass: low-resolution difference maps of every scale group + max |x| ------------------------------------
+#ifdef PISTO_X_SKIP_PREPASS
+    if (false) {
+#else
     if (multi && P >= 2) {
+#endif
       float mxf;
       if (P == 2) mxf = filter_prepass<C, V, G, 1>(g, vb, cls, ymap_s, tid, nt);
       else if (P == 3) mxf = filter_prepass<C, V, G, 2>(g, vb, cls, ymap_s, tid, nt);
@@ -734,7 +740,11 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       } else {
         exact_all = true;                   // empty (or one-class NEG_INF) presence vector
       }
+#ifdef PISTO_X_SKIP_ROWS
+      if (false) {
+#else
       if (!exact_all && worker && ys < ye) {
+#endif
         if (P == 2) filter_rows<C, G, F, NP, 1, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (P == 3) filter_rows<C, G, F, NP, 2, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (C >= 4 && P == 4) {
@@ -864,7 +874,11 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     if (LSM && multi) bar_sync(1, ncomp);  // label tile complete
 
     // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label) -----
+#ifdef PISTO_X_SKIP_VECTOR
+    if (false) {
+#else
     if (LSM || !multi) {
+#endif
       const long long base = vbase_px;
       const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
       const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
@@ -934,7 +948,9 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
         if (has_label) p.label_out[base + i] = (uint8_t)o;
       }
     }
+#ifndef PISTO_X_SKIP_EXPORT
     if (need_low) export_rows(n, sb, vb);  // whatever the export warps have not got to yet
+#endif
     if (do_conf) {
       // every lane of every compute warp reaches this point: full-mask warp reductions are safe
 #pragma unroll
