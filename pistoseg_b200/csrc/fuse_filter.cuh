@@ -44,6 +44,7 @@ constexpr int kFMaxThreads = PISTO_FTHREADS;
 constexpr int kFAux = PISTO_FAUX;  // warps that evaluate the 32x32 logit export concurrently with the row loop
 constexpr int kFQueueCap = 1024;
 constexpr int kFMaxGroups = 5;
+constexpr int K_MAX_T4 = 2;  // difference fields handled by the 4-column row loop
 
 struct FilterGeom {
   int GX, S, threads, cwarps;          // threads per output row, strips, CTA size (incl. the producer warp), compute warps
@@ -64,6 +65,7 @@ struct FilterGeom {
   unsigned int g_inv[kFMaxGroups];     // ceil(2^32 / wo): idx / wo == umulhi(idx, inv) for idx < 2^16
   float tau_coef, tau_abs;             // tau = V * max|x| * tau_coef + tau_abs
   int ctl_off, rowtab_off, rowoff_off, cola_off, colb_off, lowrow_off, lowcol_off, ymap_off, queue_off, lab_off, views_off;
+  int col4_off, col4i_off;             // 4-column tables (T4): [G][GX] float4 l1 of the thread's columns; [G][GX] u32 (4*j0 of column 0) | sel << 16
   int smem_bytes;
   int* counter;
 };
@@ -239,11 +241,17 @@ __device__ __forceinline__ void bitslice_count(const unsigned int (&gw)[8], cons
 // ---- the row loop of one strip, K difference fields ----------------------------------------------------------------
 // LSM: labels go to the shared-memory label tile (background / confusion / the global store happen in the vector pass
 // after the exact pass); otherwise they go straight to global memory with the byte masks prefetched 4 rows ahead.
-template <int C, int G, int F, int NP, int K, bool LSM>
+// T4 (NP == 2 only): the thread's 4 adjacent columns touch at most 3 adjacent source columns j, j+1, j+2 (checked on the
+// host: up-sampling by >= 3), the difference maps are stored [row][column][k] with two replicated pad columns per row, so
+// one refill is ONE 16-byte table load (the four l1 weights; l0 = 1 - l1 as in pisto_src_index) and three K-wide data loads
+// instead of 2 * (2 table + 4 K data) loads: the row loop is bound by shared-memory wavefronts, not by arithmetic.
+// colA_t = address of the thread's l1 entry, colB_t = address of its (4*j0 | sel << 16) entry; group stride 16 * GX / 4 * GX.
+template <int C, int G, int F, int NP, int K, bool LSM, bool T4 = false>
 __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeom& g, FCtl* ctl, uint32_t* queue, int b,
                                             uint32_t rowtab_s, uint32_t rowoff_s, uint32_t colA_t, uint32_t colB_t, uint32_t ymap_s,
                                             uint32_t lab_s, int n, int x, int ys, int ye, const int (&cls)[C], float tau,
                                             u64& cnt_lo, u64& cnt_hi) {
+  static_assert(!T4 || (NP == 2 && K <= 2), "4-column tables: NP == 2, K <= 2");
   constexpr bool RT = F < 0;
   constexpr int RS = 16 * ((G + 2) / 2);
   const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
@@ -257,8 +265,42 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   for (int k = 0; k < 4; k++) c4[k] = 0x01010101u * (unsigned)cls[k < C ? k : 0];
 
   u64 Hb[G][K][NP], Dh[G][K][NP], base[K][NP];
+  uint32_t yb[G];        // T4: address of (row 0, source column of the thread's first column, k = 0) of group gi's map
+  unsigned int selm = 0; // T4: bit 4*gi + c: column c reads source columns (j+1, j+2) instead of (j, j+1)
+  if (T4) {
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+      const uint32_t u = lds_u32(colB_t + gi * 4u * g.GX);
+      yb[gi] = ymap_s + g.g_ybytes[gi] + K * (u & 0xffffu);
+      selm |= (u >> 16) << (4 * gi);
+    }
+  }
+  const u64 one2 = pack2(1.f, 1.f);
   // horizontally interpolated values of one row (byte offset `row` inside a map) of every difference map of group gi
   auto load_h = [&](int gi, uint32_t row, u64 (&H)[K][NP]) {
+    if constexpr (T4) {
+      const uint32_t a = yb[gi] + K * row;
+      const float4 L1 = lds_f4(colA_t + gi * 16u * g.GX);
+      const u64 l1a = pack2(L1.x, L1.y), l1b = pack2(L1.z, L1.w);
+      const u64 l0a = sub2(one2, l1a), l0b = sub2(one2, l1b);
+      const bool s1 = (selm >> (4 * gi + 1)) & 1u, s2 = (selm >> (4 * gi + 2)) & 1u, s3 = (selm >> (4 * gi + 3)) & 1u;
+      float y0[K], y1[K], y2[K];
+      if constexpr (K == 1) {
+        y0[0] = lds_f32(a); y1[0] = lds_f32(a + 4u); y2[0] = lds_f32(a + 8u);
+      } else {
+        const float2 v0 = lds_f2(a), v1 = lds_f2(a + 8u), v2 = lds_f2(a + 16u);
+        y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float a1 = s1 ? y1[k] : y0[k], b1 = s1 ? y2[k] : y1[k];
+        const float a2 = s2 ? y1[k] : y0[k], b2 = s2 ? y2[k] : y1[k];
+        const float a3 = s3 ? y1[k] : y0[k], b3 = s3 ? y2[k] : y1[k];
+        H[k][0] = fma2(l0a, pack2(y0[k], a1), mul2(l1a, pack2(y1[k], b1)));
+        H[k][NP - 1] = fma2(l0b, pack2(a2, a3), mul2(l1b, pack2(b2, b3)));
+      }
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < NP; q++) {
       const int4 A = lds_i4(colA_t + gi * colg + 16u * q);
@@ -404,9 +446,12 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
 // frame; returns the thread's max |x| (NaN-propagating).  When every group is a (view 2g, view 2g+1) pair -- a scale and its
 // flipped twin, the BASELINE layout -- both views are read in one sweep; otherwise the first view of a group writes and the
 // others add (a thread always revisits its own cells, so the read-modify-write needs no synchronisation).
-template <int C, int V, int G, int K>
+// Map rows carry two pad columns that replicate the last one (the right-edge clamp of the 3-tap loads of filter_rows<T4>);
+// IL: the K maps of a group are interleaved [row][column][k], otherwise planar [k][row][column].
+template <int C, int V, int G, int K, bool IL>
 __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint32_t (&vb)[V], const int (&cls)[C], uint32_t ymap_s, int tid, int nt) {
   float mxf = 0.f;
+  constexpr uint32_t ES = IL ? 4u * K : 4u;  // bytes between horizontally adjacent cells
   if constexpr (V == 2 * G) {
 #pragma unroll
     for (int gi = 0; gi < G; gi++) {
@@ -427,13 +472,16 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
         const uint32_t aa = basea + i * ra + j * ca, ab = baseb + i * rb + j * cb;
         const float x0a = lds_f32(aa), x0b = lds_f32(ab);
         mxf = max_nan(max_nan(mxf, fabsf(x0a)), fabsf(x0b));
-        uint32_t ya = ym + 4u * idx;
+        uint32_t ya = ym + ES * (uint32_t)(i * (wo + 2) + j);
+        const bool last = j == wo - 1;
 #pragma unroll
         for (int q = 0; q < K; q++) {
           const float xa = lds_f32(aa + dqa[q]), xb = lds_f32(ab + dqb[q]);
           mxf = max_nan(max_nan(mxf, fabsf(xa)), fabsf(xb));
-          sts_f32(ya, __fadd_rn(__fsub_rn(xa, x0a), __fsub_rn(xb, x0b)));
-          ya += 4u * cells;
+          const float yv = __fadd_rn(__fsub_rn(xa, x0a), __fsub_rn(xb, x0b));
+          sts_f32(ya, yv);
+          if (last) { sts_f32(ya + ES, yv); sts_f32(ya + 2u * ES, yv); }
+          ya += IL ? 4u : (uint32_t)g.g_mapbytes[gi];
         }
       }
     }
@@ -454,7 +502,8 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
         const uint32_t a = base0 + i * vrow + j * vcol;
         const float x0 = lds_f32(a);
         mxf = max_nan(mxf, fabsf(x0));
-        uint32_t ya = ym + 4u * idx;
+        uint32_t ya = ym + ES * (uint32_t)(i * (wo + 2) + j);
+        const bool last = j == wo - 1;
 #pragma unroll
         for (int q = 0; q < K; q++) {
           const float xq = lds_f32(a + dq[q]);
@@ -462,7 +511,8 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
           float t = __fsub_rn(xq, x0);
           if (!first) t = __fadd_rn(lds_f32(ya), t);
           sts_f32(ya, t);
-          ya += 4u * cells;
+          if (last) { sts_f32(ya + ES, t); sts_f32(ya + 2u * ES, t); }
+          ya += IL ? 4u : (uint32_t)g.g_mapbytes[gi];
         }
       }
     }
@@ -478,6 +528,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   int2* rowoff = reinterpret_cast<int2*>(smem_raw + g.rowoff_off);        // [T_h][G] byte offsets of rows i0, i1 inside a map
   int4* colA = reinterpret_cast<int4*>(smem_raw + g.cola_off);            // [G][GXP] byte offsets {j0,j1 of col 0; j0,j1 of col 1}
   float4* colB = reinterpret_cast<float4*>(smem_raw + g.colb_off);        // [G][GXP] {l0 col0, l0 col1, l1 col0, l1 col1}
+  float4* col4 = reinterpret_cast<float4*>(smem_raw + g.col4_off);        // [G][GX] l1 of the thread's 4 columns (T4)
+  uint32_t* col4i = reinterpret_cast<uint32_t*>(smem_raw + g.col4i_off);  // [G][GX] (4 * j0 of column 0) | sel << 16 (T4)
   float4* lowrow = reinterpret_cast<float4*>(smem_raw + g.lowrow_off);    // [low_h][V] {l0, l1, byte offset i0, byte offset i1} in the RAW view
   float4* lowcol = reinterpret_cast<float4*>(smem_raw + g.lowcol_off);    // [low_w][V]
   float* ymap = reinterpret_cast<float*>(smem_raw + g.ymap_off);          // [G][C-1][ho][wo] difference maps
@@ -488,6 +540,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int T_h = p.T_h, T_w = p.T_w;
   constexpr bool RT = F < 0;
+  constexpr bool T4 = NP == 2;          // 4-column tables + interleaved maps for K <= 2 (K = 3: two NP = 1 passes, pair tables)
+  constexpr bool PAIRTAB = !T4 || C >= 4;
   constexpr int RS = 16 * ((G + 2) / 2);
   const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
   const bool do_conf = RT ? (p.conf != nullptr && p.gt != nullptr) : ((F & 2) != 0);
@@ -515,7 +569,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     for (int gi = 0; gi < G; gi++) {
       const Lerp L = pisto_src_index(g.g_scale_h[gi], y, g.g_ho[gi], false);
       reinterpret_cast<float2*>(row)[gi] = make_float2(-L.l0, -L.l0);
-      rowoff[y * G + gi] = make_int2(4 * L.i0 * g.g_wo[gi], 4 * L.i1 * g.g_wo[gi]);
+      rowoff[y * G + gi] = make_int2(4 * L.i0 * (g.g_wo[gi] + 2), 4 * L.i1 * (g.g_wo[gi] + 2));
       if (!strip_start) {  // first row of a strip: both source rows are loaded before the row loop
         const Lerp P = pisto_src_index(g.g_scale_h[gi], y - 1, g.g_ho[gi], false);
         if (P.i0 != L.i0 || P.i1 != L.i1) f |= 1u << gi;  // up-sampling: the pair moves down by exactly one row
@@ -523,13 +577,26 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     }
     reinterpret_cast<uint2*>(row)[G] = make_uint2(f, 0u);
   }
-  for (int i = tid; i < G * g.GXP; i += nthreads) {
-    const int gi = i / g.GXP, gx = i - gi * g.GXP;
-    const Lerp L0 = pisto_src_index(g.g_scale_w[gi], 2 * gx, g.g_wo[gi], g.g_same_w[gi]);
-    const Lerp L1 = pisto_src_index(g.g_scale_w[gi], 2 * gx + 1, g.g_wo[gi], g.g_same_w[gi]);
-    colA[i] = make_int4(4 * L0.i0, 4 * L0.i1, 4 * L1.i0, 4 * L1.i1);
-    colB[i] = make_float4(L0.l0, L1.l0, L0.l1, L1.l1);
-  }
+  if (PAIRTAB)
+    for (int i = tid; i < G * g.GXP; i += nthreads) {
+      const int gi = i / g.GXP, gx = i - gi * g.GXP;
+      const Lerp L0 = pisto_src_index(g.g_scale_w[gi], 2 * gx, g.g_wo[gi], g.g_same_w[gi]);
+      const Lerp L1 = pisto_src_index(g.g_scale_w[gi], 2 * gx + 1, g.g_wo[gi], g.g_same_w[gi]);
+      colA[i] = make_int4(4 * L0.i0, 4 * L0.i1, 4 * L1.i0, 4 * L1.i1);
+      colB[i] = make_float4(L0.l0, L1.l0, L0.l1, L1.l1);
+    }
+  if (T4)
+    for (int i = tid; i < G * g.GX; i += nthreads) {
+      const int gi = i / g.GX, gx = i - gi * g.GX;
+      Lerp L[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) L[c] = pisto_src_index(g.g_scale_w[gi], 4 * gx + c, g.g_wo[gi], g.g_same_w[gi]);
+      col4[i] = make_float4(L[0].l1, L[1].l1, L[2].l1, L[3].l1);
+      unsigned int sel = 0;
+#pragma unroll
+      for (int c = 1; c < 4; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;  // 0 or 1 (make_filter_geom checked)
+      col4i[i] = (unsigned)(4 * L[0].i0) | (sel << 16);
+    }
   if (need_low) {
     for (int i = tid; i < p.low_h * V; i += nthreads) {
       const int ly = i / V, v = i - ly * V;
@@ -677,7 +744,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   const int ys = g.strip_y0[strip];
   const int ye = g.strip_y0[strip + 1];
   const uint32_t rowtab_s = smem_u32(smem_raw + g.rowtab_off), rowoff_s = smem_u32(rowoff), ymap_s = smem_u32(ymap);
-  const uint32_t colA_t = smem_u32(colA) + 16u * NP * grp, colB_t = smem_u32(colB) + 16u * NP * grp;
+  const uint32_t colA_t = smem_u32(colA) + 16u * NP * grp, colB_t = smem_u32(colB) + 16u * NP * grp;  // pair tables
+  const uint32_t col4_t = smem_u32(col4) + 16u * grp, col4i_t = smem_u32(col4i) + 4u * grp;              // 4-column tables
   const uint32_t lab_s = smem_u32(labsm);
   const int nt = ncomp;  // cooperative loops below run over the compute threads only
   const long long tpx = (long long)T_h * T_w;
@@ -720,9 +788,9 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
     if (multi && P >= 2) {
 #endif
       float mxf;
-      if (P == 2) mxf = filter_prepass<C, V, G, 1>(g, vb, cls, ymap_s, tid, nt);
-      else if (P == 3) mxf = filter_prepass<C, V, G, 2>(g, vb, cls, ymap_s, tid, nt);
-      else mxf = filter_prepass<C, V, G, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      if (P == 2) mxf = filter_prepass<C, V, G, 1, T4>(g, vb, cls, ymap_s, tid, nt);
+      else if (P == 3) mxf = filter_prepass<C, V, G, 2, T4>(g, vb, cls, ymap_s, tid, nt);
+      else mxf = filter_prepass<C, V, G, (C >= 4 ? 3 : 1), false>(g, vb, cls, ymap_s, tid, nt);
       unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));  // NaN (0x7fffffff) > Inf > finite
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
@@ -745,8 +813,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 #else
       if (!exact_all && worker && ys < ye) {
 #endif
-        if (P == 2) filter_rows<C, G, F, NP, 1, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-        else if (P == 3) filter_rows<C, G, F, NP, 2, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        if (P == 2) filter_rows<C, G, F, NP, 1, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        else if (P == 3) filter_rows<C, G, F, NP, 2, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (C >= 4 && P == 4) {
           // three difference fields for four columns do not fit the register file: two passes of two columns each
           constexpr int K3 = C >= 4 ? 3 : 1;
@@ -974,6 +1042,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, int nbuf, FilterGeom* g) {
+  const bool t4 = NP == 2, pairtab = !t4 || p.C >= 4;
   memset(g, 0, sizeof(*g));
   g->nbuf = nbuf;
   if (nbuf == 1 && p.lowres_out && p.low_fh > 0) return false;  // the export reads the staged views for the whole tile
@@ -1008,6 +1077,19 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
     g->vcol[v] = 4 * (vw.map.aj * vw.w + vw.map.bj);
   }
   if (G != G_expected) return false;
+  if (t4)  // the 4 columns of a thread must lie within two adjacent source cells (3-tap loads), offsets must fit 16 bits
+    for (int q = 0; q < G; q++) {
+      if (4 * K_MAX_T4 * (g->g_wo[q] + 2) > 65535) return false;
+      for (int x = 0; x < p.T_w; x += 4) {
+        const Lerp L0 = pisto_src_index(g->g_scale_w[q], x, g->g_wo[q], g->g_same_w[q]);
+        for (int c = 0; c < 4; c++) {
+          const Lerp L = pisto_src_index(g->g_scale_w[q], x + c, g->g_wo[q], g->g_same_w[q]);
+          if (L.i0 < L0.i0 || L.i0 > L0.i0 + 1) return false;
+          if (L.i1 != L.i0 && L.i1 != L.i0 + 1) return false;
+          if (L.i1 == L.i0 && L.i0 != g->g_wo[q] - 1 && L.l1 != 0.f) return false;  // only the right-edge clamp repeats a column
+        }
+      }
+    }
   if (p.V == 2 * G)  // the paired pre-pass assumes views (2g, 2g+1) form group g
     for (int v = 0; v < p.V; v++)
       if (g->group_of[v] != v / 2) return false;
@@ -1053,14 +1135,16 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
   g->rowtab_off = off; off += RS * p.T_h;
   g->rowoff_off = off; off += 8 * G * p.T_h; off = (off + 15) & ~15;
-  g->cola_off = off; off += 16 * G * g->GXP;
-  g->colb_off = off; off += 16 * G * g->GXP;
+  g->cola_off = off; off += pairtab ? 16 * G * g->GXP : 0;
+  g->colb_off = off; off += pairtab ? 16 * G * g->GXP : 0;
+  g->col4_off = off; off += t4 ? 16 * G * GX : 0;
+  g->col4i_off = off; off += t4 ? 4 * G * GX : 0; off = (off + 15) & ~15;
   g->lowrow_off = off; off += 16 * p.V * (low ? p.low_h : 0);
   g->lowcol_off = off; off += 16 * p.V * (low ? p.low_w : 0);
   g->ymap_off = off;
   for (int q = 0; q < G; q++) {
     g->g_ybytes[q] = off - g->ymap_off;
-    g->g_mapbytes[q] = 4 * g->g_ho[q] * g->g_wo[q];
+    g->g_mapbytes[q] = 4 * g->g_ho[q] * (g->g_wo[q] + 2);  // two pad columns per row
     off += (p.C - 1) * g->g_mapbytes[q];
     off = (off + 15) & ~15;
   }
@@ -1119,7 +1203,9 @@ static int pisto_launch_filter_f(pisto_ctx* h, const FuseParams& p, cudaStream_t
       rc = launch_filter<C, V, G, F, 2, true, 1>(h, p, st, launched);
       if (rc != PISTO_OK || *launched) return rc;
     }
-    return launch_filter<C, V, G, F, 2, false, 2>(h, p, st, launched);
+    rc = launch_filter<C, V, G, F, 2, false, 2>(h, p, st, launched);
+    if (rc != PISTO_OK || *launched) return rc;
+    // e.g. views up-sampled by less than 3 (a thread's 4 columns span more than two source cells): 2 columns per thread
   }
   return launch_filter<C, V, G, -1, 1, false, 2>(h, p, st, launched);
 }
