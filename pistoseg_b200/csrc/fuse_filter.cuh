@@ -42,9 +42,13 @@ constexpr int kFMaxThreads = PISTO_FTHREADS;
 #define PISTO_FAUX 2
 #endif
 constexpr int kFAux = PISTO_FAUX;  // warps that evaluate the 32x32 logit export concurrently with the row loop
+// CTA size: three difference fields for four columns (C = 4, every class present) need ~140 registers per thread; a register-file
+// partition (16384 registers, every 4th warp) holds 3 warps of up to 168 registers, so the CTA is 12 warps
+template <int C> constexpr int filter_threads() { return C >= 4 ? 384 : kFMaxThreads; }
+// export warps: none when the feature mask is known at compile time and has no 32x32 export
+template <int F> constexpr int filter_aux() { return (F >= 0 && !(F & 8)) ? 0 : kFAux; }
 constexpr int kFQueueCap = 1024;
 constexpr int kFMaxGroups = 5;
-constexpr int K_MAX_T4 = 2;  // difference fields handled by the 4-column row loop
 
 struct FilterGeom {
   int GX, S, threads, cwarps;          // threads per output row, strips, CTA size (incl. the producer warp), compute warps
@@ -58,6 +62,7 @@ struct FilterGeom {
   int first_in_group[PISTO_MAX_VIEWS];
   int buf_floats;
   int nbuf;                            // staging buffers: 2, or 1 (views released after the pre-pass, exact pass reads global memory)
+  int aux;                             // export warps
   int g_ho[kFMaxGroups], g_wo[kFMaxGroups], g_same_w[kFMaxGroups];
   float g_scale_h[kFMaxGroups], g_scale_w[kFMaxGroups];
   int g_ybytes[kFMaxGroups];           // byte offset of group g's first difference map inside the Y area
@@ -251,7 +256,8 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
                                             uint32_t rowtab_s, uint32_t rowoff_s, uint32_t colA_t, uint32_t colB_t, uint32_t ymap_s,
                                             uint32_t lab_s, int n, int x, int ys, int ye, const int (&cls)[C], float tau,
                                             u64& cnt_lo, u64& cnt_hi) {
-  static_assert(!T4 || (NP == 2 && K <= 2), "4-column tables: NP == 2, K <= 2");
+  static_assert(!T4 || (NP == 2 && K <= 3), "4-column tables: NP == 2, K <= 3");
+  constexpr int KP = K == 3 ? 4 : K;  // floats per cell of an interleaved map
   constexpr bool RT = F < 0;
   constexpr int RS = 16 * ((G + 2) / 2);
   const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
@@ -271,7 +277,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
 #pragma unroll
     for (int gi = 0; gi < G; gi++) {
       const uint32_t u = lds_u32(colB_t + gi * 4u * g.GX);
-      yb[gi] = ymap_s + g.g_ybytes[gi] + K * (u & 0xffffu);
+      yb[gi] = ymap_s + g.g_ybytes[gi] + KP * (u & 0xffffu);
       selm |= (u >> 16) << (4 * gi);
     }
   }
@@ -279,7 +285,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   // horizontally interpolated values of one row (byte offset `row` inside a map) of every difference map of group gi
   auto load_h = [&](int gi, uint32_t row, u64 (&H)[K][NP]) {
     if constexpr (T4) {
-      const uint32_t a = yb[gi] + K * row;
+      const uint32_t a = yb[gi] + KP * row;
       const float4 L1 = lds_f4(colA_t + gi * 16u * g.GX);
       const u64 l1a = pack2(L1.x, L1.y), l1b = pack2(L1.z, L1.w);
       const u64 l0a = sub2(one2, l1a), l0b = sub2(one2, l1b);
@@ -287,9 +293,13 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
       float y0[K], y1[K], y2[K];
       if constexpr (K == 1) {
         y0[0] = lds_f32(a); y1[0] = lds_f32(a + 4u); y2[0] = lds_f32(a + 8u);
-      } else {
+      } else if constexpr (K == 2) {
         const float2 v0 = lds_f2(a), v1 = lds_f2(a + 8u), v2 = lds_f2(a + 16u);
         y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+      } else {
+        const float4 v0 = lds_f4(a), v1 = lds_f4(a + 16u), v2 = lds_f4(a + 32u);
+        y0[0] = v0.x; y0[1 % K] = v0.y; y0[K - 1] = v0.z; y1[0] = v1.x; y1[1 % K] = v1.y; y1[K - 1] = v1.z;
+        y2[0] = v2.x; y2[1 % K] = v2.y; y2[K - 1] = v2.z;
       }
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -451,7 +461,7 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
 template <int C, int V, int G, int K, bool IL>
 __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint32_t (&vb)[V], const int (&cls)[C], uint32_t ymap_s, int tid, int nt) {
   float mxf = 0.f;
-  constexpr uint32_t ES = IL ? 4u * K : 4u;  // bytes between horizontally adjacent cells
+  constexpr uint32_t ES = IL ? 4u * (K == 3 ? 4 : K) : 4u;  // bytes between horizontally adjacent cells (interleaved K = 3: padded to 4 floats)
   if constexpr (V == 2 * G) {
 #pragma unroll
     for (int gi = 0; gi < G; gi++) {
@@ -521,8 +531,7 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
 }
 
 template <int C, int V, int G, int F, int NP, bool LSM, int NB>
-__global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __grid_constant__ FuseParams p,
-                                                                      const __grid_constant__ FilterGeom g) {
+__device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const FilterGeom& g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FCtl* ctl = reinterpret_cast<FCtl*>(smem_raw + g.ctl_off);
   int2* rowoff = reinterpret_cast<int2*>(smem_raw + g.rowoff_off);        // [T_h][G] byte offsets of rows i0, i1 inside a map
@@ -540,8 +549,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int T_h = p.T_h, T_w = p.T_w;
   constexpr bool RT = F < 0;
-  constexpr bool T4 = NP == 2;          // 4-column tables + interleaved maps for K <= 2 (K = 3: two NP = 1 passes, pair tables)
-  constexpr bool PAIRTAB = !T4 || C >= 4;
+  constexpr bool T4 = NP == 2;          // 4-column tables + interleaved maps
+  constexpr bool PAIRTAB = !T4;
   constexpr int RS = 16 * ((G + 2) / 2);
   const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
   const bool do_conf = RT ? (p.conf != nullptr && p.gt != nullptr) : ((F & 2) != 0);
@@ -553,8 +562,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   if (tid == 0) {
     mbar_init(&ctl->full[0], 1);
     mbar_init(&ctl->full[1], 1);
-    mbar_init(&ctl->empty[0], g.cwarps + (need_low ? kFAux : 0));
-    mbar_init(&ctl->empty[1], g.cwarps + (need_low ? kFAux : 0));
+    mbar_init(&ctl->empty[0], g.cwarps + (need_low ? g.aux : 0));
+    mbar_init(&ctl->empty[1], g.cwarps + (need_low ? g.aux : 0));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     ctl->maxbits[0] = ctl->maxbits[1] = 0u;
     ctl->qcount[0] = ctl->qcount[1] = 0u;
@@ -645,10 +654,10 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
 
   __syncthreads();  // barriers + tables visible to every warp
 
-  const int ncomp = g.cwarps * 32;  // compute threads, then kFAux export warps; the last warp of the CTA is the producer
-  if (tid >= ncomp + 32 * kFAux) {
+  const int ncomp = g.cwarps * 32;  // compute threads, then g.aux export warps; the last warp of the CTA is the producer
+  if (tid >= ncomp + 32 * g.aux) {
     // ===== producer warp: claims tiles, publishes their ids, fetches their views (TMA) one tile ahead of the compute warps
-    if (tid == ncomp + 32 * kFAux) {
+    if (tid == ncomp + 32 * g.aux) {
       const long long tile_px = (long long)T_h * T_w;
       // the tile id (global atomic) and its presence vector are fetched one step ahead, so that only the TMA itself sits
       // between a staging buffer becoming free and its refill
@@ -790,7 +799,7 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
       float mxf;
       if (P == 2) mxf = filter_prepass<C, V, G, 1, T4>(g, vb, cls, ymap_s, tid, nt);
       else if (P == 3) mxf = filter_prepass<C, V, G, 2, T4>(g, vb, cls, ymap_s, tid, nt);
-      else mxf = filter_prepass<C, V, G, (C >= 4 ? 3 : 1), false>(g, vb, cls, ymap_s, tid, nt);
+      else mxf = filter_prepass<C, V, G, (C >= 4 ? 3 : 1), T4>(g, vb, cls, ymap_s, tid, nt);
       unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));  // NaN (0x7fffffff) > Inf > finite
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
@@ -816,14 +825,8 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
         if (P == 2) filter_rows<C, G, F, NP, 1, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (P == 3) filter_rows<C, G, F, NP, 2, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (C >= 4 && P == 4) {
-          // three difference fields for four columns do not fit the register file: two passes of two columns each
           constexpr int K3 = C >= 4 ? 3 : 1;
-          if (NP == 2) {
-            filter_rows<C, G, F, 1, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-            filter_rows<C, G, F, 1, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t + 16u, colB_t + 16u, ymap_s, lab_s, n, x + 2, ys, ye, cls, tau, cnt_lo, cnt_hi);
-          } else {
-            filter_rows<C, G, F, NP, K3, LSM>(p, g, ctl, queue, b, rowtab_s, rowoff_s, colA_t, colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-          }
+          filter_rows<C, G, F, NP, K3, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         }
       }
       bar_sync(1, ncomp);  // every strip done: the queue is complete
@@ -1038,18 +1041,31 @@ __global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __gr
   }
 }
 
+// two entry points over the same body: 512 threads x 128 registers, and (C = 4: three difference fields for four columns)
+// 384 threads x up to 168 registers
+template <int C, int V, int G, int F, int NP, bool LSM, int NB>
+__global__ void __launch_bounds__(kFMaxThreads, 1) fuse_filter_kernel(const __grid_constant__ FuseParams p,
+                                                                      const __grid_constant__ FilterGeom g) {
+  fuse_filter_body<C, V, G, F, NP, LSM, NB>(p, g);
+}
+template <int C, int V, int G, int F, int NP, bool LSM, int NB>
+__global__ void __launch_bounds__(384, 1) fuse_filter_kernel_wide(const __grid_constant__ FuseParams p, const __grid_constant__ FilterGeom g) {
+  fuse_filter_body<C, V, G, F, NP, LSM, NB>(p, g);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, int nbuf, FilterGeom* g) {
-  const bool t4 = NP == 2, pairtab = !t4 || p.C >= 4;
+static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, int G_expected, bool lsm, int nbuf, int max_threads, int aux, FilterGeom* g) {
+  const bool t4 = NP == 2, pairtab = !t4;
   memset(g, 0, sizeof(*g));
   g->nbuf = nbuf;
   if (nbuf == 1 && p.lowres_out && p.low_fh > 0) return false;  // the export reads the staged views for the whole tile
   if (p.T_w % (2 * NP)) return false;
   const int GX = p.T_w / (2 * NP);
-  if (GX > kFMaxThreads - 32 - 32 * kFAux) return false;  // one producer warp, kFAux export warps
-  int S = (kFMaxThreads - 32 - 32 * kFAux) / GX;
+  g->aux = aux;
+  if (GX > max_threads - 32 - 32 * aux) return false;  // one producer warp, aux export warps
+  int S = (max_threads - 32 - 32 * aux) / GX;
   if (S > p.T_h) S = p.T_h;
   if (S > 32) S = 32;
   // scale groups: views with the same de-augmented size share their interpolation weights
@@ -1079,7 +1095,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   if (G != G_expected) return false;
   if (t4)  // the 4 columns of a thread must lie within two adjacent source cells (3-tap loads), offsets must fit 16 bits
     for (int q = 0; q < G; q++) {
-      if (4 * K_MAX_T4 * (g->g_wo[q] + 2) > 65535) return false;
+      if (4 * 4 * (g->g_wo[q] + 2) > 65535) return false;
       for (int x = 0; x < p.T_w; x += 4) {
         const Lerp L0 = pisto_src_index(g->g_scale_w[q], x, g->g_wo[q], g->g_same_w[q]);
         for (int c = 0; c < 4; c++) {
@@ -1112,7 +1128,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   }
   g->GX = GX; g->S = S; g->GXP = p.T_w / 2; g->lab_stride = p.T_w;
   g->cwarps = (GX * S + 31) / 32;
-  g->threads = g->cwarps * 32 + 32 * kFAux + 32;
+  g->threads = g->cwarps * 32 + 32 * aux + 32;
   int rps = 0;
   for (int q = 0; q <= S; q++) g->strip_y0[q] = (int)((long long)p.T_h * q / S);
   for (int q = 0; q < S; q++) rps = max(rps, g->strip_y0[q + 1] - g->strip_y0[q]);
@@ -1145,7 +1161,7 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
   for (int q = 0; q < G; q++) {
     g->g_ybytes[q] = off - g->ymap_off;
     g->g_mapbytes[q] = 4 * g->g_ho[q] * (g->g_wo[q] + 2);  // two pad columns per row
-    off += (p.C - 1) * g->g_mapbytes[q];
+    off += ((t4 && p.C == 4) ? 4 : p.C - 1) * g->g_mapbytes[q];  // interleaved K = 3 cells are padded to 4 floats
     off = (off + 15) & ~15;
   }
   g->queue_off = off; off += 4 * kFQueueCap;
@@ -1160,8 +1176,10 @@ static bool make_filter_geom(const pisto_ctx* h, const FuseParams& p, int NP, in
 template <int C, int V, int G, int F, int NP, bool LSM, int NB>
 int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   FilterGeom g;
-  if (!make_filter_geom(h, p, NP, G, LSM, NB, &g)) return PISTO_OK;  // not launched: caller falls back
-  auto kern = fuse_filter_kernel<C, V, G, F, NP, LSM, NB>;
+  if (!make_filter_geom(h, p, NP, G, LSM, NB, filter_threads<C>(), filter_aux<F>(), &g)) return PISTO_OK;  // not launched: caller falls back
+  void (*kern)(FuseParams, FilterGeom);
+  if constexpr (C >= 4) kern = fuse_filter_kernel_wide<C, V, G, F, NP, LSM, NB>;
+  else kern = fuse_filter_kernel<C, V, G, F, NP, LSM, NB>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
@@ -1197,9 +1215,10 @@ static inline int pisto_filter_groups(const FuseParams& p) {
 template <int C, int V, int G, int F>
 static int pisto_launch_filter_f(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   if (np == 2) {
-    int rc = launch_filter<C, V, G, F, 2, true, 2>(h, p, st, launched);
+    static const bool force_direct = getenv("PISTO_FILTER_DIRECT") != nullptr;  // A/B knob: labels straight to global memory
+    int rc = force_direct ? PISTO_OK : launch_filter<C, V, G, F, 2, true, 2>(h, p, st, launched);
     if (rc != PISTO_OK || *launched) return rc;
-    if constexpr ((F & 8) == 0) {  // label tile + ONE staging buffer (never with the 32x32 export, which reads the views all tile long)
+    if constexpr ((F & 8) == 0) if (!force_direct) {  // label tile + ONE staging buffer (never with the 32x32 export, which reads the views all tile long)
       rc = launch_filter<C, V, G, F, 2, true, 1>(h, p, st, launched);
       if (rc != PISTO_OK || *launched) return rc;
     }
