@@ -232,6 +232,17 @@ int pisto_mosaic_plan_cells(pisto_handle_t h, uint64_t seed, int64_t first_index
                             int patch_size, int P, const int32_t* pool_hw, const uint16_t* integral, const int64_t* integral_off,
                             int bg_label, int max_tries, pisto_mosaic_cell_t* cells /* [N][4][patch_num^2] */, pisto_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------------- */
+/* background mask of RGB tiles: replaces utils.get_background (utils.py:155-163) and                 */
+/* BaseDataset._get_background (dataset.py:100-109):                                                  */
+/*   gray = cv2.cvtColor(RGB2GRAY) (8-bit fixed point); binary = gray > thresh (200);                 */
+/*   4-connected components with fewer than min_size (50) pixels are cleared                          */
+/*   (skimage.morphology.remove_small_objects(connectivity=1)); mask = 255 where kept, else 0.        */
+/*   rgb [N][H][W][3] u8, mask_out [N][H][W] u8, scratch int32 [2*N*H*W] (labels + component sizes).   */
+/* -------------------------------------------------------------------------------------------------- */
+int pisto_get_background(pisto_handle_t h, const uint8_t* rgb, int N, int H, int W, int thresh, int min_size,
+                         int32_t* scratch, uint8_t* mask_out, pisto_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

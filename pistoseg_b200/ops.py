@@ -297,3 +297,18 @@ def mosaic_gather(pool, plans, cells, patch_num, patch_size, bg_label=3, packed=
                                            _ptr(pool["label"]), _ptr(plans), _ptr(cells), N, patch_num, patch_size, int(bg_label),
                                            _ptr(img), _ptr(mask), _stream(dev)))
     return img, mask
+
+
+def get_background(rgb, thresh=200, min_size=50):
+    """rgb: CUDA uint8 [N,H,W,3] (or [H,W,3]) -> uint8 [N,H,W] (or [H,W]) in {0, 255}: gray > thresh with 4-connected
+    components smaller than min_size removed (utils.py:155-163, dataset.py:100-109)."""
+    if not rgb.is_cuda or rgb.dtype != torch.uint8 or rgb.shape[-1] != 3 or rgb.dim() not in (3, 4):
+        raise _lib.PistoError("get_background: expected a CUDA uint8 tensor [N,H,W,3] or [H,W,3]")
+    single = rgb.dim() == 3
+    x = (rgb[None] if single else rgb).contiguous()
+    N, H, W = x.shape[:3]
+    dev = _dev_index(x)
+    out = torch.empty((N, H, W), dtype=torch.uint8, device=x.device)
+    scratch = torch.empty(2 * N * H * W, dtype=torch.int32, device=x.device)
+    _lib.check(_lib.load().pisto_get_background(_lib.handle(dev), _ptr(x), N, H, W, int(thresh), int(min_size), _ptr(scratch), _ptr(out), _stream(dev)))
+    return out[0] if single else out

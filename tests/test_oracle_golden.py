@@ -123,3 +123,18 @@ def test_warp_affine_restatement_matches_live_cv2():
         M = wa.shift_scale_rotate_matrix(S, S, rng.uniform(-45, 45), rng.uniform(0.8, 1.2), rng.uniform(-.0625, .0625), rng.uniform(-.0625, .0625))
         assert np.array_equal(wa.warp_affine_u8(img, M), cv2.warpAffine(img, M, (S, S), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101))
         assert np.array_equal(wa.warp_affine_u8(msk, M, nearest=True), cv2.warpAffine(msk, M, (S, S), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_REFLECT_101))
+
+
+def test_background_oracle_known_cases():
+    """oracle/background.py: cv2 gray/threshold + restated remove_small_objects (4-connectivity, size < 50 removed)."""
+    from oracle import background as obg
+    img = np.zeros((40, 40, 3), np.uint8)
+    img[0:7, 0:7] = 255            # 49 pixels: removed
+    img[10:15, 10:20] = 255        # 50 pixels: kept
+    img[15, 20] = 255              # diagonal neighbour of the 50-pixel block: not 4-connected, removed
+    img[30:32, 0:40] = (201, 201, 201)  # gray 201 > 200: 80 pixels kept
+    img[35:37, 0:40] = (200, 200, 200)  # gray 200: not background
+    m = obg.get_background(img)
+    assert m.dtype == np.uint8 and set(np.unique(m)) == {0, 255}
+    assert m[0:7, 0:7].sum() == 0 and (m[10:15, 10:20] == 255).all() and m[15, 20] == 0
+    assert (m[30:32] == 255).all() and m[35:37].sum() == 0
