@@ -9,13 +9,18 @@
 // copied block-wise, along THEIR rows, into padded shared-memory tiles and then read transposed from there.  The per-pixel sum
 // runs in view order (bit-exact with the sequential merge), followed by pisto_decide / confusion / background / exports
 // as in every other fusion kernel.
+#include <stdlib.h>
+#include <string.h>
+
 #include "fuse_common.cuh"
+#include "sm100_prims.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kB = 32;        // block side
 constexpr int kPad = kB + 1;  // shared-memory row pitch (floats)
+constexpr int kPT = kB + 4;   // pipelined kernel, transposing views: 16-byte aligned rows, column reads hit 8 banks (4-way conflict)
 
 template <int C>
 __global__ void __launch_bounds__(kThreads) fuse_fullres_kernel(const __grid_constant__ FuseParams p, int nby, int nbx, int n_transposed) {
@@ -133,6 +138,276 @@ __global__ void __launch_bounds__(kThreads) fuse_fullres_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Pipelined variant (the one that runs for the BASELINE shapes): one persistent CTA per SM; the V*C planes of a 32x32 output
+// block are brought into shared memory with 16-byte cp.async chunks -- source columns are stored as they lie in memory and
+// read back mirrored (flips) or transposed (rot90 / rot270: a 4-way bank conflict that does not matter at this arithmetic
+// intensity) -- two blocks deep, so ~100 KB of loads are in flight per SM while the previous block is summed.  The byte masks
+// ride along in the same cp.async group.  Measured alternatives: 4-byte cp.async into 33-float-pitch tiles for the transposing
+// views (40 % of the HBM peak), one 128-byte 1-D TMA copy per source-row segment (18 %: too many small bulk copies).
+// Same arithmetic as above: sum in view order, pisto_decide.
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kPThreads = 512;  // pipelined kernel: 16 warps, two output rows per thread
+
+struct FullresPlan {
+  int nby, nbx;
+  int view_off[PISTO_MAX_VIEWS];       // float offset of view v's first plane inside a stage
+  int bg_off, gt_off;                  // float offsets of the 32x32 byte blocks of bg / gt inside a stage
+  int stage_floats;
+  unsigned int inv_fh, inv_fw;         // ceil(2^32 / low_fh), ceil(2^32 / low_fw): y / low_fh == umulhi(y, inv_fh) for y < 2^16
+  unsigned int inv_nbx;                // ceil(2^32 / nbx)
+};
+
+// x / d for x < 2^16 with inv = ceil(2^32 / d); d == 1 has no 32-bit inverse
+__device__ __forceinline__ int fastdiv(int x, int d, unsigned int inv) { return d == 1 ? x : (int)__umulhi((unsigned)x, inv); }
+
+// (tile, block row, block column) of a CTA's current item, advanced by gridDim.x items without divisions
+struct ItemPos {
+  int n, rem;
+  __device__ __forceinline__ void advance(int step_n, int step_rem, int per_tile) {
+    n += step_n; rem += step_rem;
+    if (rem >= per_tile) { rem -= per_tile; n++; }
+  }
+};
+
+template <int C, int V>
+__global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ FullresPlan pl) {
+  extern __shared__ __align__(16) float stage_mem[];  // [2][stage_floats]
+  __shared__ unsigned int hist[C * C];
+  constexpr int BINS = C * C;
+  constexpr int VH = (V + 1) / 2;      // views whose copies a thread issues (threads 0..255: even views, 256..511: odd views)
+  constexpr int RPT = kB * kB / kPThreads;  // output rows per thread (2)
+  const bool do_conf = p.conf != nullptr && p.gt != nullptr;
+  const bool has_bg = p.bg != nullptr && p.label_out != nullptr;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // rows ty, ty + 16
+  for (int i = tid; i < BINS; i += kPThreads) hist[i] = 0;
+  const int T_h = p.T_h, T_w = p.T_w;
+  const long long hw = (long long)T_h * T_w;
+  const int per_tile = pl.nby * pl.nbx;
+  const bool need_low = p.lowres_out != nullptr && p.low_fh > 0;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_mem);
+  const int step_n = (int)gridDim.x / per_tile, step_rem = (int)gridDim.x - step_n * per_tile;
+
+  // Copies: 16-byte cp.async chunks, thread = (tile row r, chunk q) of every plane of its views.  Tile row r of a row-preserving
+  // view is the source row of output row y0 + r; tile row r of a transposing view is the source row of output COLUMN x0 + r.
+  // Either way the tile holds 32 consecutive source columns as they lie in memory.
+  // element offset of the thread's chunk inside a tile = koff + by * kdy + bx * kdx
+  const int cr = (tid >> 3) & 31, cq = tid & 7, vpar = tid >> 8;
+  int koff[VH], kdy[VH], kdx[VH], planes[VH];
+#pragma unroll
+  for (int j = 0; j < VH; j++) {
+    const int v = 2 * j + vpar < V ? 2 * j + vpar : 0;
+    const ViewDev& vw = p.view[v];
+    const ViewMap& m = vw.map;
+    planes[j] = vw.h * vw.w;
+    if (m.ai != 0) {
+      koff[j] = (m.a0 + cr * m.ai) * vw.w + (m.bj > 0 ? m.b0 : m.b0 - (kB - 1)) + 4 * cq;
+      kdy[j] = kB * m.ai * vw.w;
+      kdx[j] = m.bj > 0 ? kB : -kB;
+    } else {
+      koff[j] = (m.a0 + cr * m.aj) * vw.w + (m.bi > 0 ? m.b0 : m.b0 - (kB - 1)) + 4 * cq;
+      kdy[j] = m.bi > 0 ? kB : -kB;
+      kdx[j] = kB * m.aj * vw.w;
+    }
+  }
+  auto presence_of = [&](const ItemPos& ip) {
+    TilePresence t; t.bits = 0xffffffffu; t.single = -1;
+    if (ip.n < p.N) t = pisto_tile_presence(p, ip.n);
+    return t;
+  };
+  auto issue = [&](const ItemPos& ip, int s, const TilePresence& tp) {
+    const int n = ip.n;
+    const int by = fastdiv(ip.rem, pl.nbx, pl.inv_nbx), bx = ip.rem - by * pl.nbx;
+    const int y0 = by * kB, x0 = bx * kB;
+    const uint32_t sbase = smem0 + 4u * (uint32_t)(s * pl.stage_floats);
+    const bool full = y0 + kB <= T_h && x0 + kB <= T_w;
+    if (vpar == 0 && y0 + cr < T_h && x0 + 4 * cq < T_w) {  // byte masks: 32 rows x 32 bytes, one 4-byte chunk per thread
+      const long long o = (long long)n * hw + (long long)(y0 + cr) * T_w + x0 + 4 * cq;
+      if (has_bg) cp_async4(sbase + 4u * (uint32_t)pl.bg_off + (uint32_t)(cr * kB + 4 * cq), p.bg + o);
+      if (do_conf) cp_async4(sbase + 4u * (uint32_t)pl.gt_off + (uint32_t)(cr * kB + 4 * cq), p.gt + o);
+    }
+    if (!(tp.single < 0 || p.fused_out || need_low)) return;  // single-label tile whose scores nobody wants
+#pragma unroll
+    for (int j = 0; j < VH; j++) {
+      const int v = 2 * j + vpar;
+      if (v >= V) break;
+      const ViewDev& vw = p.view[v];
+      const ViewMap& m = vw.map;
+      const int pitch = m.ai != 0 ? kB : kPT;
+      bool ok = true;
+      if (!full) {
+        int col;
+        if (m.ai != 0) { col = (m.bj > 0 ? m.b0 + x0 : m.b0 - x0 - (kB - 1)) + 4 * cq; ok = y0 + cr < T_h; }
+        else { col = (m.bi > 0 ? m.b0 + y0 : m.b0 - y0 - (kB - 1)) + 4 * cq; ok = x0 + cr < T_w; }
+        ok = ok && col >= 0 && col + 3 < vw.w;
+      }
+      if (ok) {
+        const float* g = vw.logits + (long long)n * vw.tile_stride + (koff[j] + by * kdy[j] + bx * kdx[j]);
+        const uint32_t d = sbase + 4u * (uint32_t)(pl.view_off[v] + cr * pitch + 4 * cq);
+#pragma unroll
+        for (int c = 0; c < C; c++) cp_async16(d + 4u * (uint32_t)(c * kB * pitch), g + c * planes[j]);
+      }
+    }
+  };
+
+  ItemPos cur, nxt, nx2;
+  cur.n = (int)blockIdx.x / per_tile; cur.rem = (int)blockIdx.x - cur.n * per_tile;
+  nxt = cur; nxt.advance(step_n, step_rem, per_tile);
+  nx2 = nxt; nx2.advance(step_n, step_rem, per_tile);
+  TilePresence tp_cur = presence_of(cur), tp_next = presence_of(nxt);
+  if (cur.n < p.N) issue(cur, 0, tp_cur);
+  cp_async_commit();
+  int s = 0;
+  for (; cur.n < p.N; s ^= 1) {
+    const TilePresence tp_next2 = presence_of(nx2);  // requested two items ahead of its use
+    if (nxt.n < p.N) issue(nxt, s ^ 1, tp_next);
+    cp_async_commit();
+    cp_async_wait<1>();   // this item's group has landed (the next item's may still be in flight)
+    __syncthreads();
+    const int n = cur.n;
+    const int by = fastdiv(cur.rem, pl.nbx, pl.inv_nbx), bx = cur.rem - by * pl.nbx;
+    const int y0 = by * kB, x0 = bx * kB;
+    const TilePresence tp = tp_cur;
+    const bool need_scores = tp.single < 0 || p.fused_out || need_low;
+    const float* st = stage_mem + s * pl.stage_floats;
+    float acc[RPT][C];
+    if (need_scores) {
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const ViewMap& m = p.view[v].map;
+        const float* vb = st + pl.view_off[v];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+          const int row = ty + 16 * r;
+          int idx, cstride;
+          if (m.ai != 0) { idx = row * kB + (m.bj > 0 ? tx : kB - 1 - tx); cstride = kB * kB; }
+          else { idx = tx * kPT + (m.bi > 0 ? row : kB - 1 - row); cstride = kB * kPT; }  // 4-way bank conflict: negligible here
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            const float val = vb[idx + c * cstride];
+            acc[r][c] = (v == 0) ? val : __fadd_rn(acc[r][c], val);
+          }
+        }
+      }
+    }
+    const uint8_t* bgs = reinterpret_cast<const uint8_t*>(st + pl.bg_off);
+    const uint8_t* gts = reinterpret_cast<const uint8_t*>(st + pl.gt_off);
+    unsigned long long lo = 0, hi = 0;
+    const int xx = x0 + tx;
+    bool lowx = false; int lxq = 0;
+    if (need_low) { lxq = fastdiv(xx, p.low_fw, pl.inv_fw); lowx = xx - lxq * p.low_fw == p.low_fw / 2; }
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const int yy = y0 + ty + 16 * r;
+      if (yy < T_h && xx < T_w) {
+        const long long rpix = (long long)yy * T_w + xx, pix = (long long)n * hw + rpix;
+        if (p.fused_out) {
+#pragma unroll
+          for (int c = 0; c < C; c++) p.fused_out[((long long)n * C + c) * hw + rpix] = pisto_div_views(acc[r][c], p.dec);
+        }
+        if (lowx) {
+          const int lyq = fastdiv(yy, p.low_fh, pl.inv_fh);
+          if (yy - lyq * p.low_fh == p.low_fh / 2) {
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              p.lowres_out[(((long long)n * C + c) * p.low_h + lyq) * p.low_w + lxq] = pisto_div_views(acc[r][c], p.dec);
+          }
+        }
+        int lab;
+        if (tp.single >= 0) lab = tp.single;
+        else lab = pisto_decide<C>(acc[r], tp.bits, p.dec, false, nullptr);
+        if (do_conf) {
+          const unsigned int gg = gts[(ty + 16 * r) * kB + tx];
+          if (gg < (unsigned)C) {
+            const unsigned int bn = gg * C + lab;
+            const unsigned long long inc = 1ull << (8 * (bn & 7));
+            if (bn < 8) lo += inc; else hi += inc;
+          }
+        }
+        if (p.label_out) {
+          unsigned int o = (unsigned)lab;
+          if (has_bg && bgs[(ty + 16 * r) * kB + tx] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+          p.label_out[pix] = (uint8_t)o;
+        }
+      }
+    }
+    if (do_conf) {
+#pragma unroll
+      for (int b = 0; b < BINS; b++) {
+        unsigned int v = (unsigned int)(((b < 8 ? lo : hi) >> (8 * (b & 7))) & 0xffull);
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (tx == 0 && v) atomicAdd(&hist[b], v);
+      }
+    }
+    tp_cur = tp_next; tp_next = tp_next2;
+    cur = nxt; nxt = nx2; nx2.advance(step_n, step_rem, per_tile);
+    __syncthreads();  // stage s is refilled two iterations from now, by copies issued after this barrier
+  }
+  cp_async_wait<0>();
+  if (do_conf) {
+    __syncthreads();
+    for (int i = tid; i < BINS; i += kPThreads)
+      if (hist[i]) atomicAdd(&p.conf[i], (unsigned long long)hist[i]);
+  }
+}
+
+template <int C, int V>
+static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  static_assert(C <= 4, "packed 8-bit confusion counters");
+  if (p.T_w % 4 || p.T_h > 65535 || p.T_w > 65535) return PISTO_OK;
+  if ((((uintptr_t)p.bg | (uintptr_t)p.gt) & 3) || (((long long)p.T_h * p.T_w) % 4)) return PISTO_OK;  // 4-byte chunks of the byte masks
+  FullresPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  int fl = 0;
+  for (int v = 0; v < V; v++) {
+    const ViewDev& vw = p.view[v];
+    if (((uintptr_t)vw.logits & 15) || (vw.w % 4) || (vw.tile_stride % 4)) return PISTO_OK;  // 16-byte chunks
+    if ((long long)vw.h * vw.w * 4 > 0x7fffffffLL / 8) return PISTO_OK;                      // 32-bit element offsets inside a tile
+    pl.view_off[v] = fl;
+    fl += C * kB * (vw.map.ai != 0 ? kB : kPT);
+  }
+  pl.bg_off = fl; fl += kB * kB / 4;
+  pl.gt_off = fl; fl += kB * kB / 4;
+  pl.stage_floats = fl;
+  if (p.low_fh > 0 && p.low_fw > 0) {
+    pl.inv_fh = (unsigned int)(((1ull << 32) + p.low_fh - 1) / p.low_fh);
+    pl.inv_fw = (unsigned int)(((1ull << 32) + p.low_fw - 1) / p.low_fw);
+  }
+  const size_t smem = 2 * (size_t)fl * sizeof(float);
+  if (smem > (size_t)h->smem_optin - 2048) return PISTO_OK;
+  pl.nby = (p.T_h + kB - 1) / kB;
+  pl.nbx = (p.T_w + kB - 1) / kB;
+  pl.inv_nbx = (unsigned int)(((1ull << 32) + pl.nbx - 1) / pl.nbx);
+  const long long items = (long long)p.N * pl.nby * pl.nbx;
+  if (items > 0x7fffffffLL / 2) return PISTO_OK;
+  const int grid = (int)(items < h->sm_count ? items : h->sm_count);
+  PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fuse_fullres_pipe_kernel<C, V><<<grid, kPThreads, smem, st>>>(p, pl);
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
+  *launched = true;
+  return PISTO_OK;
+}
+
+template <int C>
+static int launch_fullres_pipe_c(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  switch (p.V) {
+    case 2: return launch_fullres_pipe<C, 2>(h, p, st, launched);   // hflip_transform
+    case 4: return launch_fullres_pipe<C, 4>(h, p, st, launched);   // flips / rot180
+    case 8: return launch_fullres_pipe<C, 8>(h, p, st, launched);   // d4_transform (infer_pseudo_masks.py:96)
+    default: return PISTO_OK;
+  }
+}
+
 }  // namespace
 
 int pisto_launch_fuse_fullres(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
@@ -144,6 +419,13 @@ int pisto_launch_fuse_fullres(pisto_ctx* h, const FuseParams& p, cudaStream_t st
     const ViewDev& vw = p.view[v];
     if (!(vw.same_h && vw.same_w)) return PISTO_OK;
     if (vw.map.ai == 0) ntr++;
+  }
+  if (!getenv("PISTO_FULLRES_OLD")) {  // pipelined kernel first (A/B knob: the single-stage kernel below)
+    int rc = PISTO_OK;
+    if (p.C == 2) rc = launch_fullres_pipe_c<2>(h, p, st, launched);
+    else if (p.C == 3) rc = launch_fullres_pipe_c<3>(h, p, st, launched);
+    else if (p.C == 4) rc = launch_fullres_pipe_c<4>(h, p, st, launched);
+    if (rc != PISTO_OK || *launched) return rc;
   }
   const size_t smem = (size_t)ntr * p.C * kB * kPad * sizeof(float);
   if (smem > (size_t)h->smem_optin - 2048) return PISTO_OK;

@@ -237,7 +237,7 @@ def test_identity_view_fast_path_equals_generic(cuda, C):
                 assert torch.equal(a["conf"], b["conf"]), (C, mask, decide)
 
 
-@pytest.mark.parametrize("T,C", [((224, 224), 3), ((96, 120), 4), ((70, 45), 3)])
+@pytest.mark.parametrize("T,C", [((224, 224), 3), ((96, 120), 4), ((70, 45), 3), ((100, 120), 3), ((64, 32), 2), ((224, 224), 4)])
 def test_fullres_d4_kernel_equals_generic_and_oracle(cuda, T, C):
     """ttach d4 on full-resolution logits (the literal infer_pseudo_masks.py path): the streaming full-resolution kernel
     (automatic dispatch) == the generic kernel == the oracle, for fused scores, labels, 32x32 export and confusion."""
