@@ -37,11 +37,16 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
   };
   // all lanes of a warp run the same number of iterations (flush uses full-mask warp reductions)
   const long long warp_base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+  // (tile, group inside the tile) of the lane's current 4-pixel group, advanced without 64-bit divisions
+  const long long q0 = warp_base + (threadIdx.x & 31);
+  int n = (int)(q0 / q_per_tile);
+  long long rq = q0 - (long long)n * q_per_tile;
+  const int step_n = (int)(stride / q_per_tile);
+  const long long step_r = stride - (long long)step_n * q_per_tile;
   for (long long qb = warp_base; qb < total; qb += stride) {
     const long long q = qb + (threadIdx.x & 31);
     if (q < total) {
-      const int n = (int)(q / q_per_tile);
-      const long long r4 = (q - (long long)n * q_per_tile) * 4;   // first pixel of the group inside the tile
+      const long long r4 = rq * 4;   // first pixel of the group inside the tile
       const TilePresence tp = pisto_tile_presence(p, n);
       int lab[4];
       if (tp.single >= 0) {
@@ -91,6 +96,8 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
       }
     }
+    n += step_n; rq += step_r;
+    if (rq >= q_per_tile) { rq -= q_per_tile; n++; }
     pending += 4;
     if (do_conf && pending > 255 - 4) flush();
   }
