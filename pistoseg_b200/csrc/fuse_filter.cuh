@@ -79,6 +79,8 @@ struct FCtl {
   uint64_t full[2];   // producer -> consumers: tile id published (+ TMA bytes landed)
   uint64_t empty[2];  // consumers -> producer: staging buffer may be refilled (one arrival per compute warp)
   int tile[2];
+  unsigned int pres_bits[2];  // class-presence summary of the published tile (read from global memory by the producer, one tile ahead)
+  int pres_single[2];
   unsigned int maxbits[2];  // max |x| of the tile (IEEE bits; NaN > Inf > finite), slot = tile parity
   unsigned int qcount[2];   // uncertain pixels queued by the row loop
   unsigned int lownext[2];  // next low-resolution row of the logit export to be claimed (any warp may claim)
@@ -621,11 +623,6 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
     }
   }
 
-  // does tile n read its views at all?  (single-label tiles without the 32x32 export do not)
-  auto tile_needs_views = [&](int n) -> bool {
-    if (need_low) return true;
-    return pisto_tile_presence(p, n).single < 0;
-  };
   // producer lane: fetch every view of tile n into staging buffer b
   auto issue_tile = [&](int n, int b) {
     float* buf = vsm + b * g.buf_floats;
@@ -662,12 +659,16 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
       // the tile id (global atomic) and its presence vector are fetched one step ahead, so that only the TMA itself sits
       // between a staging buffer becoming free and its refill
       int next = atomicAdd(g.counter, 1);
-      bool next_views = next < p.N && tile_needs_views(next);
+      TilePresence next_tp; next_tp.bits = 0u; next_tp.single = -1;
+      if (next < p.N) next_tp = pisto_tile_presence(p, next);
+      bool next_views = next < p.N && (need_low || next_tp.single < 0);
       for (int k = 0;; k++) {
         const int b = NB == 2 ? (k & 1) : 0;
         if (k >= NB) mbar_wait_sleep(&ctl->empty[b], NB == 2 ? (((k >> 1) - 1) & 1) : ((k - 1) & 1));  // every warp is done with buffer b
         const int tile = next < p.N ? next : -1;
         ctl->tile[b] = tile;
+        ctl->pres_bits[b] = next_tp.bits;
+        ctl->pres_single[b] = next_tp.single;
         ctl->lownext[b] = 0u;
         if (tile >= 0 && next_views) issue_tile(tile, b);
         else mbar_arrive(&ctl->full[b]);
@@ -678,7 +679,8 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
           if (do_conf && ((uintptr_t)p.gt & 15) == 0) bulk_prefetch_l2(p.gt + tile * tile_px, (uint32_t)tile_px);
         }
         next = atomicAdd(g.counter, 1);
-        next_views = next < p.N && tile_needs_views(next);
+        if (next < p.N) next_tp = pisto_tile_presence(p, next);
+        next_views = next < p.N && (need_low || next_tp.single < 0);
       }
     }
     return;
@@ -765,7 +767,10 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
     mbar_wait(&ctl->full[sb], NB == 2 ? ((k >> 1) & 1) : (k & 1));  // tile id published, views (if any) landed
     const int n = ctl->tile[sb];
     if (n < 0) break;
-    const TilePresence tp = pisto_tile_presence(p, n);
+    TilePresence tp = pisto_tile_presence(p, n);   // no present vector: constants
+    if (p.present) {                               // published by the producer with the tile id: no global-memory latency here
+      tp.bits = ctl->pres_bits[sb]; tp.single = ctl->pres_single[sb];
+    }
     const bool multi = tp.single < 0;
     // shared-memory byte address of view v's data in this tile's staging buffer (incl. the 0..3-float alignment shift)
     uint32_t vb[V];
