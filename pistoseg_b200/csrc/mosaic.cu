@@ -152,7 +152,7 @@ __device__ __noinline__ PixOut mosaic_pixel_slow(const MosaicParams& p, const Ce
 // A tap is then two map loads, one 16-byte cell entry and one multiply-add.  The INTER_NEAREST mask tap is always one of the
 // four INTER_LINEAR taps (floor((Z + 512) / 1024) - floor((Z + 16) / 1024) is 0 or 1), so it costs no extra lookup.
 template <int PS, bool RGBA>
-__global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant__ MosaicParams p) {
+__global__ void __launch_bounds__(kThreads, 4) mosaic_kernel(const __grid_constant__ MosaicParams p) {
   extern __shared__ __align__(16) unsigned char msm[];
   const int S = p.S, pn = p.pn, pn2 = pn * pn, S3 = 3 * p.S;
   const int ps = PS > 0 ? PS : p.ps;
@@ -209,16 +209,12 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
     }
     __syncthreads();
     const int sh = plan->split_h, sw = plan->split_w;
+    const unsigned int inv_gpr = (unsigned int)((0x100000000ull + groups_per_row - 1) / groups_per_row);  // groups_per_row > 1
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-      const int Y = it / groups_per_row, gx = it - Y * groups_per_row;
+      const int Y = groups_per_row > 1 ? (int)__umulhi((unsigned)it, inv_gpr) : it, gx = it - Y * groups_per_row;
       unsigned int rgb[4], mask_bytes[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int X = gx * 4 + k;
-        const int q = (Y >= sh ? 2 : 0) + (X >= sw ? 1 : 0);
-        const pisto_mosaic_quad_t* qd = &plan->quad[q];
-        const int yc = (Y >= sh ? Y - sh : Y) + qd->crop_y;
-        const int xc = (X >= sw ? X - sw : X) + qd->crop_x;
+      // one output pixel, every case (the body used for groups that straddle the vertical split and for the rare slow taps)
+      auto pixel = [&](int k, int q, const pisto_mosaic_quad_t* qd, int yc, int xc) {
         const int warp = qd->warp;
         const FastEnt* fq = fents + q * pn2;
         const unsigned int* rm = rowmap + q * S3 + S;
@@ -245,33 +241,52 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
           if ((unsigned)(sx + S) >= (unsigned)(S3 - 1) || (unsigned)(sy + S) >= (unsigned)(S3 - 1)) slow = true;  // outside the index maps
           else {
             const unsigned int r0 = rm[sy], r1 = rm[sy + 1], c0 = cm[sx], c1 = cm[sx + 1];
-            const FastEnt e00 = fq[(r0 >> 16) + (c0 >> 16)], e01 = fq[(r0 >> 16) + (c1 >> 16)];
-            const FastEnt e10 = fq[(r1 >> 16) + (c0 >> 16)], e11 = fq[(r1 >> 16) + (c1 >> 16)];
-            if ((e00.label_padded | e01.label_padded | e10.label_padded | e11.label_padded) >> 8) slow = true;
-            else {
-              const int iy0 = (int)(r0 & 0xffffu), iy1 = (int)(r1 & 0xffffu), ix0 = (int)(c0 & 0xffffu), ix1 = (int)(c1 & 0xffffu);
+            const int iy0 = (int)(r0 & 0xffffu), iy1 = (int)(r1 & 0xffffu), ix0 = (int)(c0 & 0xffffu), ix1 = (int)(c1 & 0xffffu);
+            // INTER_NEAREST (mask): round_delta = 512 -> the tap (sy + dy, sx + dx), dy, dx in {0, 1}
+            const int dx = ((X0b + 512 + adelta) >> AB_BITS) - sx, dy = ((Y0b + 512 + bdelta) >> AB_BITS) - sy;
+            unsigned int v00, v01, v10, v11, m;
+            long long onear = 0;
+            if ((((r0 ^ r1) | (c0 ^ c1)) >> 16) == 0) {
+              // the four taps lie in one grid cell (all but the pixels next to a cell border): one cell entry, one address
+              const FastEnt e = fq[(r0 >> 16) + (c0 >> 16)];
+              if (e.label_padded >> 8) slow = true;
+              const long long o00 = e.base + iy0 * e.tw + ix0;
+              const int ox = ix1 - ix0, oy = (iy1 - iy0) * e.tw;
+              if (!slow) {
+                v00 = fetch_px<RGBA>(p, o00, false); v01 = fetch_px<RGBA>(p, o00 + ox, false);
+                v10 = fetch_px<RGBA>(p, o00 + oy, false); v11 = fetch_px<RGBA>(p, o00 + oy + ox, false);
+              }
+              m = e.label_padded & 0xffu;
+              onear = o00 + (dy ? oy : 0) + (dx ? ox : 0);
+            } else {
+              const FastEnt e00 = fq[(r0 >> 16) + (c0 >> 16)], e01 = fq[(r0 >> 16) + (c1 >> 16)];
+              const FastEnt e10 = fq[(r1 >> 16) + (c0 >> 16)], e11 = fq[(r1 >> 16) + (c1 >> 16)];
+              if ((e00.label_padded | e01.label_padded | e10.label_padded | e11.label_padded) >> 8) slow = true;
               const long long o00 = e00.base + iy0 * e00.tw + ix0, o01 = e01.base + iy0 * e01.tw + ix1;
               const long long o10 = e10.base + iy1 * e10.tw + ix0, o11 = e11.base + iy1 * e11.tw + ix1;
-              // 2x2 int16 weights of OpenCV's BilinearTab_i (closed form; the one saturated entry gets its fix-up)
-              int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-              if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
-              const unsigned int v00 = fetch_px<RGBA>(p, o00, false), v01 = fetch_px<RGBA>(p, o01, false);
-              const unsigned int v10 = fetch_px<RGBA>(p, o10, false), v11 = fetch_px<RGBA>(p, o11, false);
-              unsigned int out = 0;
-#pragma unroll
-              for (int ch = 0; ch < 3; ch++) {
-                int v = (int)((v00 >> (8 * ch)) & 0xffu) * w00 + (int)((v01 >> (8 * ch)) & 0xffu) * w01 + (int)((v10 >> (8 * ch)) & 0xffu) * w10 +
-                        (int)((v11 >> (8 * ch)) & 0xffu) * w11;
-                v = (v + (1 << 14)) >> 15;
-                out |= (unsigned int)(v < 0 ? 0 : (v > 255 ? 255 : v)) << (8 * ch);
+              if (!slow) {
+                v00 = fetch_px<RGBA>(p, o00, false); v01 = fetch_px<RGBA>(p, o01, false);
+                v10 = fetch_px<RGBA>(p, o10, false); v11 = fetch_px<RGBA>(p, o11, false);
               }
-              rgb[k] = out;
-              // INTER_NEAREST (mask): round_delta = 512 -> the tap (sy + dy, sx + dx), dy, dx in {0, 1}
-              const int dx = ((X0b + 512 + adelta) >> AB_BITS) - sx, dy = ((Y0b + 512 + bdelta) >> AB_BITS) - sy;
-              unsigned int m = (dy ? (dx ? e11.label_padded : e10.label_padded) : (dx ? e01.label_padded : e00.label_padded)) & 0xffu;
+              m = (dy ? (dx ? e11.label_padded : e10.label_padded) : (dx ? e01.label_padded : e00.label_padded)) & 0xffu;
+              onear = dy ? (dx ? o11 : o10) : (dx ? o01 : o00);
+            }
+            if (!slow) {
+              // OpenCV's BilinearTab_i weights are (32-fy)(32-fx)*32 ... fy*fx*32 (the one saturated entry, fx = fy = 0, reproduces
+              // the tap itself either way), so  (sum w*p + 2^14) >> 15  ==  ((32-fy)*h0 + fy*h1 + 512) >> 10  with the horizontal sums
+              // h = (32-fx)*p_left + fx*p_right <= 8160: exact integer arithmetic, red and blue ride in 16-bit lanes of one word
+              const unsigned int fx0 = 32 - fx, fy0 = 32 - fy;
+              const unsigned int h0rb = fx0 * (v00 & 0x00ff00ffu) + fx * (v01 & 0x00ff00ffu);
+              const unsigned int h1rb = fx0 * (v10 & 0x00ff00ffu) + fx * (v11 & 0x00ff00ffu);
+              const unsigned int h0g = fx0 * ((v00 >> 8) & 0xffu) + fx * ((v01 >> 8) & 0xffu);
+              const unsigned int h1g = fx0 * ((v10 >> 8) & 0xffu) + fx * ((v11 >> 8) & 0xffu);
+              const unsigned int r = (fy0 * (h0rb & 0xffffu) + fy * (h1rb & 0xffffu) + 512u) >> 10;
+              const unsigned int b = (fy0 * (h0rb >> 16) + fy * (h1rb >> 16) + 512u) >> 10;
+              const unsigned int g = (fy0 * h0g + fy * h1g + 512u) >> 10;
+              rgb[k] = r | (g << 8) | (b << 16);
               unsigned int bgbit;
               if (RGBA) bgbit = (dy ? (dx ? v11 : v10) : (dx ? v01 : v00)) >> 24;
-              else bgbit = fetch_px<RGBA>(p, dy ? (dx ? o11 : o10) : (dx ? o01 : o00), true) >> 24;
+              else bgbit = fetch_px<RGBA>(p, onear, true) >> 24;
               mask_bytes[k] = bgbit ? (unsigned)p.bg_label : m;
             }
           }
@@ -280,6 +295,16 @@ __global__ void __launch_bounds__(kThreads) mosaic_kernel(const __grid_constant_
           const PixOut o = mosaic_pixel_slow<PS, RGBA>(p, ents + q * pn2, S, pn, ps, qd->flip, warp, yc, xc, adelta, bdelta, X0b, Y0b);
           rgb[k] = o.rgb; mask_bytes[k] = o.mask;
         }
+      };
+      const int X0 = gx * 4;
+      const int qrow = Y >= sh ? 2 : 0;
+      const int ycb = Y >= sh ? Y - sh : Y;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int X = X0 + k;
+        const int q = qrow + (X >= sw ? 1 : 0);
+        const pisto_mosaic_quad_t* qd = &plan->quad[q];
+        pixel(k, q, qd, ycb + qd->crop_y, (X >= sw ? X - sw : X) + qd->crop_x);
       }
       uint32_t* io = reinterpret_cast<uint32_t*>(p.img_out + ((long long)(n * (long long)S + Y) * S + gx * 4) * 3);
       io[0] = rgb[0] | (rgb[1] << 24);
