@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FCtl* ctl = reinterpret_cast<FCtl*>(smem_raw + bg.ctl_off);
   int2* rowoff = reinterpret_cast<int2*>(smem_raw + bg.rowoff_off);
-  int4* colA = reinterpret_cast<int4*>(smem_raw + bg.cola_off);
-  float4* colB = reinterpret_cast<float4*>(smem_raw + bg.colb_off);
+  float2* col2 = reinterpret_cast<float2*>(smem_raw + bg.cola_off);     // [G][BW/2] {l1 of the pair's two columns}
+  uint32_t* col2i = reinterpret_cast<uint32_t*>(smem_raw + bg.colb_off); // [G][BW/2] (4 * first source column, relative to the block) | sel << 16
   uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + bg.queue_off);
   uint8_t* labsm = smem_raw + bg.lab_off;
   constexpr bool RT = F < 0;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
   const int grp = tid % bg.GX, strip = min(tid / bg.GX, bg.S - 1);
   const bool worker = tid < bg.GX * bg.S;
   const int xr = 4 * grp;  // first of the thread's 4 columns, relative to the block
-  const uint32_t colA_t = smem_u32(colA) + 32u * grp, colB_t = smem_u32(colB) + 32u * grp;
+  const uint32_t colA_t = smem_u32(col2) + 16u * grp, colB_t = smem_u32(col2i) + 8u * grp;  // the thread's first pair
   u64 cnt_lo = 0, cnt_hi = 0;
 
   const long long items = (long long)p.N * bg.nby * bg.nbx;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
         for (int gi = 0; gi < G; gi++) {
           const Lerp L = pisto_src_index(g.g_scale_h[gi], y0 + r, g.g_ho[gi], false);
           reinterpret_cast<float2*>(row)[gi] = make_float2(-L.l0, -L.l0);
-          const int stride = 4 * bg.ncols_cap[gi];
+          const int stride = 4 * (bg.ncols_cap[gi] + 2);  // two pad columns per map row (fuse_filter.cuh, 3-tap loads)
           rowoff[r * G + gi] = make_int2((L.i0 - ib[gi]) * stride, (L.i1 - ib[gi]) * stride);
           if (!strip_start) {
             const Lerp Q = pisto_src_index(g.g_scale_h[gi], y0 + r - 1, g.g_ho[gi], false);
@@ -133,11 +133,12 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
         const int gi = i / (BW / 2), gx = i - gi * (BW / 2);
         const Lerp L0 = pisto_src_index(g.g_scale_w[gi], x0 + 2 * gx, g.g_wo[gi], g.g_same_w[gi]);
         const Lerp L1 = pisto_src_index(g.g_scale_w[gi], x0 + 2 * gx + 1, g.g_wo[gi], g.g_same_w[gi]);
-        colA[i] = make_int4(4 * (L0.i0 - jb[gi]), 4 * (L0.i1 - jb[gi]), 4 * (L1.i0 - jb[gi]), 4 * (L1.i1 - jb[gi]));
-        colB[i] = make_float4(L0.l0, L1.l0, L0.l1, L1.l1);
+        col2[i] = make_float2(L0.l1, L1.l1);                                              // l0 = 1 - l1 (pisto_src_index)
+        col2i[i] = (unsigned)(4 * (L0.i0 - jb[gi])) | ((unsigned)((L1.i0 - L0.i0) << 1) << 16);  // up-sampling: the second column starts 0 or 1 cells later
       }
       // ---- pre-pass: summed class differences of the sub-rectangle, from global memory ---------------------------------
       float mxf = 0.f;
+      const uint32_t kp = P == 4 ? 4u : (uint32_t)(P - 1);  // floats per cell of the interleaved maps (K = 3 is padded to 4)
 #pragma unroll
       for (int gi = 0; gi < G; gi++) {
         const int ie = pisto_src_index(g.g_scale_h[gi], y1 - 1, g.g_ho[gi], false).i1;
@@ -171,7 +172,10 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
             for (int q = 0; q < C - 1; q++)
               if (q + 1 < P) {
                 mxf = max_nan(max_nan(mxf, fabsf(xa[q])), fabsf(xc[q]));
-                sts_f32(ym + q * g.g_mapbytes[gi] + 4u * (di * cap + dj), __fadd_rn(__fsub_rn(xa[q], x0a), __fsub_rn(xc[q], x0c)));
+                const float yv = __fadd_rn(__fsub_rn(xa[q], x0a), __fsub_rn(xc[q], x0c));
+                const uint32_t ya = ym + 4u * (kp * (di * (cap + 2) + dj) + q);   // [row][column][k], two pad columns per row
+                sts_f32(ya, yv);
+                if (jb[gi] + dj == g.g_wo[gi] - 1) { sts_f32(ya + 4u * kp, yv); sts_f32(ya + 8u * kp, yv); }  // right-edge clamp
               }
           }
         } else {
@@ -200,7 +204,11 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
             }
 #pragma unroll
             for (int q = 0; q < C - 1; q++)
-              if (q + 1 < P) sts_f32(ym + q * g.g_mapbytes[gi] + 4u * (di * cap + dj), y[q]);
+              if (q + 1 < P) {
+                const uint32_t ya = ym + 4u * (kp * (di * (cap + 2) + dj) + q);
+                sts_f32(ya, y[q]);
+                if (j == g.g_wo[gi] - 1) { sts_f32(ya + 4u * kp, y[q]); sts_f32(ya + 8u * kp, y[q]); }
+              }
           }
         }
       }
@@ -220,11 +228,11 @@ __global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_co
       if (!exact_all && worker && ys < ye) {
         // two passes of two columns: the register file does not hold four columns of G*K fields for G = 5
         for (int half = 0; half < 2; half++) {
-          const uint32_t ca = colA_t + 16u * half, cb = colB_t + 16u * half;
+          const uint32_t ca = colA_t + 8u * half, cb = colB_t + 4u * half;
           const int xx = xr + 2 * half;
-          if (P == 2) filter_rows<C, G, 16, 1, 1, true>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
-          else if (P == 3) filter_rows<C, G, 16, 1, 2, true>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
-          else filter_rows<C, G, 16, 1, (C >= 4 ? 3 : 1), true>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          if (P == 2) filter_rows<C, G, 16, 1, 1, true, 2>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          else if (P == 3) filter_rows<C, G, 16, 1, 2, true, 2>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          else filter_rows<C, G, 16, 1, (C >= 4 ? 3 : 1), true, 2>(p, g, ctl, queue, 0, rowtab_s, rowoff_s, ca, cb, ymap_s, lab_s, n, xx, ys, ye, cls, tau, cnt_lo, cnt_hi);
         }
       }
       __syncthreads();
@@ -310,7 +318,7 @@ int launch_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launch
   int Gn = 0, nmax = 0, cnt[kFMaxGroups] = {0};
   for (int v = 0; v < p.V; v++) {
     const ViewDev& vw = p.view[v];
-    if (vw.map.ho >= p.T_h) return PISTO_OK;
+    if (vw.map.ho >= p.T_h || vw.map.wo >= p.T_w) return PISTO_OK;  // up-sampling in both directions (3-tap pair loads)
     int gi = -1;
     for (int q = 0; q < Gn; q++)
       if (g.g_ho[q] == vw.map.ho && g.g_wo[q] == vw.map.wo) gi = q;
@@ -366,13 +374,13 @@ int launch_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launch
   b.ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
   b.rowtab_off = off; off += RS * b.BH + 16;
   b.rowoff_off = off; off += 8 * G * b.BH; off = (off + 15) & ~15;
-  b.cola_off = off; off += 16 * G * (b.BW / 2);
-  b.colb_off = off; off += 16 * G * (b.BW / 2);
+  b.cola_off = off; off += 8 * G * (b.BW / 2);
+  b.colb_off = off; off += 4 * G * (b.BW / 2); off = (off + 15) & ~15;
   b.ymap_off = off;
   for (int gi = 0; gi < G; gi++) {
     g.g_ybytes[gi] = off - b.ymap_off;
-    g.g_mapbytes[gi] = 4 * b.nrows_cap[gi] * b.ncols_cap[gi];
-    off += (p.C - 1) * g.g_mapbytes[gi];
+    g.g_mapbytes[gi] = 4 * b.nrows_cap[gi] * (b.ncols_cap[gi] + 2);
+    off += (p.C == 4 ? 4 : p.C - 1) * g.g_mapbytes[gi];
     off = (off + 15) & ~15;
   }
   b.queue_off = off; off += 4 * kFQueueCap;

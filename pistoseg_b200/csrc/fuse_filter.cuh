@@ -253,12 +253,16 @@ __device__ __forceinline__ void bitslice_count(const unsigned int (&gw)[8], cons
 // one refill is ONE 16-byte table load (the four l1 weights; l0 = 1 - l1 as in pisto_src_index) and three K-wide data loads
 // instead of 2 * (2 table + 4 K data) loads: the row loop is bound by shared-memory wavefronts, not by arithmetic.
 // colA_t = address of the thread's l1 entry, colB_t = address of its (4*j0 | sel << 16) entry; group stride 16 * GX / 4 * GX.
-template <int C, int G, int F, int NP, int K, bool LSM, bool T4 = false>
+// TT == 2 (NP == 1, the block-tiled kernel): the same layout for a column pair -- colA_t = address of the pair's {l1, l1} entry
+// (group stride 8 * GXP), colB_t = address of its (4*j0 | sel << 16) entry (group stride 4 * GXP).
+template <int C, int G, int F, int NP, int K, bool LSM, int TT = 0>
 __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeom& g, FCtl* ctl, uint32_t* queue, int b,
                                             uint32_t rowtab_s, uint32_t rowoff_s, uint32_t colA_t, uint32_t colB_t, uint32_t ymap_s,
                                             uint32_t lab_s, int n, int x, int ys, int ye, const int (&cls)[C], float tau,
                                             u64& cnt_lo, u64& cnt_hi) {
+  constexpr bool T4 = TT == 4, T2 = TT == 2;
   static_assert(!T4 || (NP == 2 && K <= 3), "4-column tables: NP == 2, K <= 3");
+  static_assert(!T2 || (NP == 1 && K <= 3), "pair 3-tap tables: NP == 1, K <= 3");
   constexpr int KP = K == 3 ? 4 : K;  // floats per cell of an interleaved map
   constexpr bool RT = F < 0;
   constexpr int RS = 16 * ((G + 2) / 2);
@@ -275,10 +279,10 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   u64 Hb[G][K][NP], Dh[G][K][NP], base[K][NP];
   uint32_t yb[G];        // T4: address of (row 0, source column of the thread's first column, k = 0) of group gi's map
   unsigned int selm = 0; // T4: bit 4*gi + c: column c reads source columns (j+1, j+2) instead of (j, j+1)
-  if (T4) {
+  if (T4 || T2) {
 #pragma unroll
     for (int gi = 0; gi < G; gi++) {
-      const uint32_t u = lds_u32(colB_t + gi * 4u * g.GX);
+      const uint32_t u = lds_u32(colB_t + gi * 4u * (T4 ? g.GX : g.GXP));
       yb[gi] = ymap_s + g.g_ybytes[gi] + KP * (u & 0xffffu);
       selm |= (u >> 16) << (4 * gi);
     }
@@ -286,6 +290,29 @@ __device__ __forceinline__ void filter_rows(const FuseParams& p, const FilterGeo
   const u64 one2 = pack2(1.f, 1.f);
   // horizontally interpolated values of one row (byte offset `row` inside a map) of every difference map of group gi
   auto load_h = [&](int gi, uint32_t row, u64 (&H)[K][NP]) {
+    if constexpr (T2) {
+      const uint32_t a = yb[gi] + KP * row;
+      const float2 L1 = lds_f2(colA_t + gi * 8u * g.GXP);
+      const u64 l1p = pack2(L1.x, L1.y), l0p = sub2(one2, l1p);
+      const bool s1 = (selm >> (4 * gi + 1)) & 1u;
+      float y0[K], y1[K], y2[K];
+      if constexpr (K == 1) {
+        y0[0] = lds_f32(a); y1[0] = lds_f32(a + 4u); y2[0] = lds_f32(a + 8u);
+      } else if constexpr (K == 2) {
+        const float2 v0 = lds_f2(a), v1 = lds_f2(a + 8u), v2 = lds_f2(a + 16u);
+        y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+      } else {
+        const float4 v0 = lds_f4(a), v1 = lds_f4(a + 16u), v2 = lds_f4(a + 32u);
+        y0[0] = v0.x; y0[1 % K] = v0.y; y0[K - 1] = v0.z; y1[0] = v1.x; y1[1 % K] = v1.y; y1[K - 1] = v1.z;
+        y2[0] = v2.x; y2[1 % K] = v2.y; y2[K - 1] = v2.z;
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const float a1 = s1 ? y1[k] : y0[k], b1 = s1 ? y2[k] : y1[k];
+        H[k][0] = fma2(l0p, pack2(y0[k], a1), mul2(l1p, pack2(y1[k], b1)));
+      }
+      return;
+    }
     if constexpr (T4) {
       const uint32_t a = yb[gi] + KP * row;
       const float4 L1 = lds_f4(colA_t + gi * 16u * g.GX);
@@ -827,11 +854,11 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
 #else
       if (!exact_all && worker && ys < ye) {
 #endif
-        if (P == 2) filter_rows<C, G, F, NP, 1, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
-        else if (P == 3) filter_rows<C, G, F, NP, 2, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        if (P == 2) filter_rows<C, G, F, NP, 1, LSM, T4 ? 4 : 0>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+        else if (P == 3) filter_rows<C, G, F, NP, 2, LSM, T4 ? 4 : 0>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         else if (C >= 4 && P == 4) {
           constexpr int K3 = C >= 4 ? 3 : 1;
-          filter_rows<C, G, F, NP, K3, LSM, T4>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
+          filter_rows<C, G, F, NP, K3, LSM, T4 ? 4 : 0>(p, g, ctl, queue, b, rowtab_s, rowoff_s, T4 ? col4_t : colA_t, T4 ? col4i_t : colB_t, ymap_s, lab_s, n, x, ys, ye, cls, tau, cnt_lo, cnt_hi);
         }
       }
       bar_sync(1, ncomp);  // every strip done: the queue is complete
