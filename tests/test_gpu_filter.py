@@ -183,3 +183,28 @@ def test_band_kernel_large_tiles(cuda, T, C, scales):
     # automatic dispatch picks it for these shapes
     c = ops.fuse_argmax_confusion(views, cfg["codes"], (T, T), present=present, bg=bg, **kw)
     assert torch.equal(c["labels"], b["labels"])
+
+
+def test_full_size_runs_through_size_independent_properties(cuda):
+    """BASELINE sizes (16 384 cfg-2 tiles in one launch, 10 000 cfg-3 tiles): the batch is a seeded block repeated, so
+    (i) every repetition must reproduce the block's labels / 32x32 logits bit for bit whichever CTA processed it and in
+    whatever order the dynamic scheduler handed tiles out, (ii) the block itself equals the exact kernel's result, (iii) the
+    confusion matrix is linear in the batch (10 x the block's matrix) and counts exactly the pixels with gt < C."""
+    base = synthetic.cfg2(N=512)
+    reps = 32
+    up = lambda t: t.to(cuda).repeat((reps,) + (1,) * (t.dim() - 1)).contiguous()
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+    out = ops.fuse_argmax_confusion([up(v) for v in base["views"]], base["codes"], (224, 224), present=up(base["present"]), bg=up(base["bg"]), **kw)
+    ref = run(base, cuda, IMPL_STREAM, **kw)
+    lab = out["labels"].view(reps, 512, 224, 224)
+    low = out["lowres"].view(reps, 512, 3, 32, 32)
+    assert torch.equal(lab[0], ref["labels"]) and torch.equal(low[0], ref["lowres"])
+    assert bool((lab == lab[0:1]).all()) and bool((low == low[0:1]).all())
+    del out, lab, low
+    b3 = synthetic.cfg3(N=1000)
+    up3 = lambda t: t.to(cuda).repeat((10,) + (1,) * (t.dim() - 1)).contiguous()
+    conf = ops.new_confusion(4, cuda)
+    ops.fuse_argmax_confusion([up3(v) for v in b3["views"]], b3["codes"], (224, 224), decide=DECIDE_SOFTMAX, gt=up3(b3["gt"]), conf=conf)
+    one = run(b3, cuda, IMPL_STREAM, decide=DECIDE_SOFTMAX, conf=ops.new_confusion(4, cuda))["conf"]
+    assert torch.equal(conf, 10 * one)
+    assert int(conf.sum().item()) == 10 * int((b3["gt"] < 4).sum().item())
