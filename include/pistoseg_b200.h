@@ -232,6 +232,13 @@ int pisto_mosaic_plan_cells(pisto_handle_t h, uint64_t seed, int64_t first_index
                             int patch_size, int P, const int32_t* pool_hw, const uint16_t* integral, const int64_t* integral_off,
                             int bg_label, int max_tries, pisto_mosaic_cell_t* cells /* [N][4][patch_num^2] */, pisto_stream_t stream);
 
+/* normalise + resize + sum over scales in one pass (segmentation_test.py:187-199, prepare_seg_inputs.py:128-134):
+ *   out[c] (+)= bilinear_f64( canvas[c] / max(count, min_count if > 0) ) resized from (hi, wi) to (ho, wo);
+ *   accumulate = 0 stores (first scale: `pred = m.copy()`), 1 adds (`pred + m`).  Operation order per value as in the reference. */
+int pisto_canvas_resize_accumulate(pisto_handle_t h, const double* canvas /* [C][hi][wi] */, const double* count /* [hi][wi] */, int C,
+                                   int hi, int wi, double min_count, double* out /* [C][ho][wo] */, int ho, int wo, int accumulate,
+                                   pisto_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------------- */
 /* background mask of RGB tiles: replaces utils.get_background (utils.py:155-163) and                 */
 /* BaseDataset._get_background (dataset.py:100-109):                                                  */

@@ -78,6 +78,7 @@ SYMBOLS = {
     "pisto_mosaic_pack_pool": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "pisto_mosaic_gather_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pisto_mosaic_bg_integral": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "pisto_canvas_resize_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _i, _i, _i, _vp]),
     "pisto_get_background": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pisto_mosaic_plan_cells": (_i, [_vp, C.c_uint64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }

@@ -2,7 +2,7 @@
 #include "fuse_common.cuh"
 
 int pisto_upsample_launch(pisto_ctx* h, const void* in, void* out, long long NC, int hi, int wi, int ho, int wo, int dtype,
-                          cudaStream_t st);
+                          cudaStream_t st, const double* count = nullptr, double min_count = 0.0, int accumulate = 0);
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 

@@ -34,10 +34,15 @@ __device__ __forceinline__ double mul_t(double a, double b) { return __dmul_rn(a
 // kept in registers (Ha: row i0, Hb: row i1) and only reloaded when the output row moves to another source-row pair, so an
 // output row costs 4 multiplies + 4 fused multiply-adds and one 16-byte (f32) / two 16-byte (f64) stores.  The expression
 // fma(ly0, fma(lx0, a, lx1*b), ly1 * fma(lx0, c, lx1*d)) and its rounding are unchanged.
-template <typename T>
+//
+// FUSED (float64 only): the big-mask epilogue of segmentation_test.py:187-199 / prepare_seg_inputs.py:128-134 in one pass --
+// every source value is canvas / count (count clamped below by min_count when > 0) formed on the fly, and the result is added
+// to `out` (accumulate) instead of stored: normalise + resize + sum over scales without the two intermediate canvases.  The
+// operations per value (one division, the bilinear expression, one addition) and their order are the reference's.
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in, T* __restrict__ out, long long NC, int hi, int wi,
                                                        int ho, int wo, T scale_h, T scale_w, int strips, int rows_per_strip, int xblocks,
-                                                       int vec_ok) {
+                                                       int vec_ok, const T* __restrict__ count, T min_count, int accumulate) {
   constexpr int PX = 4;
   const bool same_h = hi == ho, same_w = wi == wo;
   const long long nblocks = NC * strips * xblocks;
@@ -56,8 +61,19 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
     int p0 = -1, p1 = -1;
     auto load_row = [&](int i, T (&H)[PX]) {
       const T* r = plane + (long long)i * wi;
+      if constexpr (FUSED) {
+        const T* cr = count + (long long)i * wi;
+        auto tap = [&](int j) {
+          T d = __ldg(cr + j);
+          if (min_count > (T)0 && d < min_count) d = min_count;
+          return __ldg(r + j) / d;   // IEEE division (no fast-math): canvas /= count of the reference
+        };
 #pragma unroll
-      for (int k = 0; k < PX; k++) H[k] = fma_t(lx[k].l0, __ldg(r + lx[k].i0), mul_t(lx[k].l1, __ldg(r + lx[k].i1)));
+        for (int k = 0; k < PX; k++) H[k] = fma_t(lx[k].l0, tap(lx[k].i0), mul_t(lx[k].l1, tap(lx[k].i1)));
+      } else {
+#pragma unroll
+        for (int k = 0; k < PX; k++) H[k] = fma_t(lx[k].l0, __ldg(r + lx[k].i0), mul_t(lx[k].l1, __ldg(r + lx[k].i1)));
+      }
     };
     const int ys = strip * rows_per_strip, ye = min(ho, ys + rows_per_strip);
     T* o = out + (nc * ho + ys) * (long long)wo + x0;
@@ -81,6 +97,11 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
       T res[PX];
 #pragma unroll
       for (int k = 0; k < PX; k++) res[k] = fma_t(ly.l0, Ha[k], mul_t(ly.l1, Hb[k]));
+      if (FUSED && accumulate) {
+#pragma unroll
+        for (int k = 0; k < PX; k++)
+          if (x0 + k < wo) res[k] = o[k] + res[k];
+      }
       if (vec_ok) {
         if (sizeof(T) == 4) {
           *reinterpret_cast<float4*>(o) = make_float4((float)res[0], (float)res[1], (float)res[2], (float)res[3]);
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
 }  // namespace
 
 int pisto_upsample_launch(pisto_ctx* h, const void* in, void* out, long long NC, int hi, int wi, int ho, int wo, int dtype,
-                          cudaStream_t st) {
+                          cudaStream_t st, const double* count, double min_count, int accumulate) {
   if (NC == 0) return PISTO_OK;
   const int wq = (wo + 3) / 4;
   const int threads = wq >= 256 ? 256 : ((wq + 31) / 32) * 32;
@@ -117,11 +138,14 @@ int pisto_upsample_launch(pisto_ctx* h, const void* in, void* out, long long NC,
   const size_t esz = dtype == 0 ? 4 : 8;
   const int vec_ok = (wo % 4 == 0) && (((uintptr_t)out & 15) == 0) && ((wo * esz) % 16 == 0);
   if (dtype == 0)
-    upsample_kernel<float><<<(int)grid, threads, 0, st>>>((const float*)in, (float*)out, NC, hi, wi, ho, wo, (float)hi / (float)ho,
-                                                          (float)wi / (float)wo, strips, rows_per_strip, xblocks, vec_ok);
+    upsample_kernel<float, false><<<(int)grid, threads, 0, st>>>((const float*)in, (float*)out, NC, hi, wi, ho, wo, (float)hi / (float)ho,
+                                                                 (float)wi / (float)wo, strips, rows_per_strip, xblocks, vec_ok, nullptr, 0.f, 0);
+  else if (!count)
+    upsample_kernel<double, false><<<(int)grid, threads, 0, st>>>((const double*)in, (double*)out, NC, hi, wi, ho, wo, (double)hi / (double)ho,
+                                                                  (double)wi / (double)wo, strips, rows_per_strip, xblocks, vec_ok, nullptr, 0.0, 0);
   else
-    upsample_kernel<double><<<(int)grid, threads, 0, st>>>((const double*)in, (double*)out, NC, hi, wi, ho, wo, (double)hi / (double)ho,
-                                                           (double)wi / (double)wo, strips, rows_per_strip, xblocks, vec_ok);
+    upsample_kernel<double, true><<<(int)grid, threads, 0, st>>>((const double*)in, (double*)out, NC, hi, wi, ho, wo, (double)hi / (double)ho,
+                                                                 (double)wi / (double)wo, strips, rows_per_strip, xblocks, vec_ok, count, min_count, accumulate);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   return PISTO_OK;
@@ -134,5 +158,14 @@ extern "C" int pisto_upsample_bilinear(pisto_handle_t h, const void* in, void* o
   PISTO_REQUIRE(NC >= 0 && hi >= 1 && wi >= 1 && ho >= 1 && wo >= 1, "pisto_upsample_bilinear: bad shape");
   PISTO_REQUIRE(NC == 0 || (in && out), "pisto_upsample_bilinear: NULL buffer");
   PISTO_CUDA(cudaSetDevice(h->device));
-  return pisto_upsample_launch(h, in, out, NC, hi, wi, ho, wo, dtype, (cudaStream_t)stream);
+  return pisto_upsample_launch(h, in, out, NC, hi, wi, ho, wo, dtype, (cudaStream_t)stream, nullptr, 0.0, 0);
+}
+
+extern "C" int pisto_canvas_resize_accumulate(pisto_handle_t h, const double* canvas, const double* count, int C, int hi, int wi,
+                                              double min_count, double* out, int ho, int wo, int accumulate, pisto_stream_t stream) {
+  PISTO_REQUIRE(h, "pisto_canvas_resize_accumulate: NULL handle");
+  PISTO_REQUIRE(C >= 1 && hi >= 1 && wi >= 1 && ho >= 1 && wo >= 1, "pisto_canvas_resize_accumulate: bad shape");
+  PISTO_REQUIRE(canvas && count && out, "pisto_canvas_resize_accumulate: NULL buffer");
+  PISTO_CUDA(cudaSetDevice(h->device));
+  return pisto_upsample_launch(h, canvas, out, C, hi, wi, ho, wo, 1, (cudaStream_t)stream, count, min_count, accumulate);
 }

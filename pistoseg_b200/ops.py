@@ -240,6 +240,18 @@ def canvas_normalize(canvas, count=None, min_count=0.0):
     _lib.check(lib.pisto_canvas_normalize(_lib.handle(dev), _ptr(canvas), _ptr(count), C_, hw, float(min_count), _stream(dev)))
 
 
+def canvas_resize_accumulate(canvas, count, out, min_count=0.0, accumulate=True):
+    """out (+)= bilinear_f64(canvas / count) resized to out's size, in one pass (segmentation_test.py:187-199,
+    prepare_seg_inputs.py:128-134).  canvas f64 [C,hi,wi], count f64 [hi,wi], out f64 [C,ho,wo]; canvas is not modified."""
+    dev = _dev_index(canvas)
+    canvas, count = canvas.contiguous(), count.contiguous()
+    if canvas.dtype != torch.float64 or count.dtype != torch.float64 or out.dtype != torch.float64 or not out.is_contiguous():
+        raise _lib.PistoError("canvas_resize_accumulate: contiguous float64 tensors expected")
+    lib = _lib.load()
+    _lib.check(lib.pisto_canvas_resize_accumulate(_lib.handle(dev), _ptr(canvas), _ptr(count), canvas.shape[0], canvas.shape[1], canvas.shape[2],
+                                                  float(min_count), _ptr(out), out.shape[1], out.shape[2], int(bool(accumulate)), _stream(dev)))
+
+
 def canvas_axpy(out, x, scale=1.0):
     """out += x * scale (float64)."""
     dev = _dev_index(out)

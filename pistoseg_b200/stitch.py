@@ -28,11 +28,13 @@ class BigMaskFuser:
 
     def fused(self):
         """[C,h,w] float64: mean over scales of the normalised, resized canvases (segmentation_test.py:187-204)."""
-        total = torch.zeros((self.C, self.h, self.w), dtype=torch.float64, device=self.device)
-        for key, canvas in self.canvas.items():
-            ops.canvas_normalize(canvas, self.count[key])
-            ops.canvas_axpy(total, ops.upsample_bilinear(canvas, (self.h, self.w)))
-        ops.canvas_normalize(total, None, float(len(self.canvas)))
+        total = torch.empty((self.C, self.h, self.w), dtype=torch.float64, device=self.device)
+        for i, (key, canvas) in enumerate(self.canvas.items()):
+            # canvas / count, float64 bilinear to the image size and the sum over scales in one pass; the canvases stay as they are
+            ops.canvas_resize_accumulate(canvas, self.count[key], total, accumulate=i > 0)
+        if not self.canvas:
+            total.zero_()
+        ops.canvas_normalize(total, None, float(max(len(self.canvas), 1)))
         return total
 
     def finish(self, gt=None, conf=None, bg_match=3, bg_label=3):
@@ -53,7 +55,6 @@ def cam_ensemble(cams_per_scale, positions_per_scale, scales, image_wh, side=224
         canvas = torch.zeros((C, w_, h_), dtype=torch.float64, device=device)
         count = torch.zeros((w_, h_), dtype=torch.float64, device=device)
         ops.stitch_accumulate(crops, [[y, x, ix, iy] for y, x in positions_per_scale[s]], canvas, count, softmax=False)
-        ops.canvas_normalize(canvas, count, 1.0)                        # sum_counter[sum_counter < 1] = 1
-        ops.canvas_axpy(ens, ops.upsample_bilinear(canvas, (w, h)))
+        ops.canvas_resize_accumulate(canvas, count, ens, min_count=1.0)  # sum_counter[sum_counter < 1] = 1; /; resize; ensemble +=
     ops.canvas_normalize(ens, None, float(len(scales)))
     return ens
