@@ -17,13 +17,17 @@ class BigMaskFuser:
         self.canvas, self.count = {}, {}
 
     def add_tiles(self, logits, scale, positions, crops):
-        """logits CUDA f32 [n,C,Hp,Wp]; positions [(y, x)]; crops [(orig_h, orig_w)]  (segmentation_test.py:145-174)."""
+        """logits CUDA f32 [n,C,Hp,Wp]; positions [(y, x)]; crops [(orig_h, orig_w)]  (segmentation_test.py:145-174);
+        or positions = CUDA int32 [n,4] rows (y, x, crop_h, crop_w) with crops=None."""
         key = float(scale)
         if key not in self.canvas:
             hs, ws = int(self.h * scale), int(self.w * scale)
             self.canvas[key] = torch.zeros((self.C, hs, ws), dtype=torch.float64, device=self.device)
             self.count[key] = torch.zeros((hs, ws), dtype=torch.float64, device=self.device)
-        pos = [[p[0], p[1], c[0], c[1]] for p, c in zip(positions, crops)]
+        if torch.is_tensor(positions) and positions.is_cuda:
+            pos = positions                       # prebuilt int32 [n,4] (y, x, crop_h, crop_w) on the device: a fixed tile grid can be cached
+        else:
+            pos = [[p[0], p[1], c[0], c[1]] for p, c in zip(positions, crops)]
         ops.stitch_accumulate(logits, pos, self.canvas[key], self.count[key], softmax=True)
 
     def fused(self):

@@ -111,7 +111,8 @@ for sc in scales_:
     if ys[-1] != hs - 224: ys.append(hs - 224)
     if xs[-1] != ws - 224: xs.append(ws - 224)
     pos = [(y, x) for y in ys for x in xs]
-    tiles_[sc] = torch.randn((len(pos), 3, 224, 224), generator=g).to(dev); poss_[sc] = pos; crops_[sc] = [(224, 224)] * len(pos)
+    tiles_[sc] = torch.randn((len(pos), 3, 224, 224), generator=g).to(dev); crops_[sc] = None
+    poss_[sc] = torch.tensor([[y, x, 224, 224] for y, x in pos], dtype=torch.int32, device=dev)   # fixed tile grid: built once
     tile_bytes += tiles_[sc].numel() * 4
 gt_ = torch.randint(0, 4, (H_, W_), generator=g, dtype=torch.uint8).to(dev)
 
