@@ -156,7 +156,10 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kPThreads = 512;  // pipelined kernel: 16 warps, two output rows per thread
+#ifndef PISTO_FR_THREADS
+#define PISTO_FR_THREADS 512
+#endif
+constexpr int kPThreads = PISTO_FR_THREADS;  // pipelined kernel: 16 warps, two output rows per thread
 
 struct FullresPlan {
   int nby, nbx;
@@ -184,8 +187,10 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   extern __shared__ __align__(16) float stage_mem[];  // [2][stage_floats]
   __shared__ unsigned int hist[C * C];
   constexpr int BINS = C * C;
-  constexpr int VH = (V + 1) / 2;      // views whose copies a thread issues (threads 0..255: even views, 256..511: odd views)
-  constexpr int RPT = kB * kB / kPThreads;  // output rows per thread (2)
+  constexpr int VPAR = kPThreads / 256;     // copy teams of 256 threads: team t issues the copies of views t, t + VPAR, ...
+  constexpr int VH = (V + VPAR - 1) / VPAR;
+  constexpr int RPT = kB * kB / kPThreads;  // output rows per thread
+  constexpr int RSTEP = kPThreads / 32;     // rows between a thread's output rows
   const bool do_conf = p.conf != nullptr && p.gt != nullptr;
   const bool has_bg = p.bg != nullptr && p.label_out != nullptr;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // rows ty, ty + 16
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   int koff[VH], kdy[VH], kdx[VH], planes[VH];
 #pragma unroll
   for (int j = 0; j < VH; j++) {
-    const int v = 2 * j + vpar < V ? 2 * j + vpar : 0;
+    const int v = VPAR * j + vpar < V ? VPAR * j + vpar : 0;
     const ViewDev& vw = p.view[v];
     const ViewMap& m = vw.map;
     planes[j] = vw.h * vw.w;
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
     if (!(tp.single < 0 || p.fused_out || need_low)) return;  // single-label tile whose scores nobody wants
 #pragma unroll
     for (int j = 0; j < VH; j++) {
-      const int v = 2 * j + vpar;
+      const int v = VPAR * j + vpar;
       if (v >= V) break;
       const ViewDev& vw = p.view[v];
       const ViewMap& m = vw.map;
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
         const float* vb = st + pl.view_off[v];
 #pragma unroll
         for (int r = 0; r < RPT; r++) {
-          const int row = ty + 16 * r;
+          const int row = ty + RSTEP * r;
           int idx, cstride;
           if (m.ai != 0) { idx = row * kB + (m.bj > 0 ? tx : kB - 1 - tx); cstride = kB * kB; }
           else { idx = tx * kPT + (m.bi > 0 ? row : kB - 1 - row); cstride = kB * kPT; }  // 4-way bank conflict: negligible here
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
     if (need_low) { lxq = fastdiv(xx, p.low_fw, pl.inv_fw); lowx = xx - lxq * p.low_fw == p.low_fw / 2; }
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
-      const int yy = y0 + ty + 16 * r;
+      const int yy = y0 + ty + RSTEP * r;
       if (yy < T_h && xx < T_w) {
         const long long rpix = (long long)yy * T_w + xx, pix = (long long)n * hw + rpix;
         if (p.fused_out) {
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
         if (tp.single >= 0) lab = tp.single;
         else lab = pisto_decide<C>(acc[r], tp.bits, p.dec, false, nullptr);
         if (do_conf) {
-          const unsigned int gg = gts[(ty + 16 * r) * kB + tx];
+          const unsigned int gg = gts[(ty + RSTEP * r) * kB + tx];
           if (gg < (unsigned)C) {
             const unsigned int bn = gg * C + lab;
             const unsigned long long inc = 1ull << (8 * (bn & 7));
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
         }
         if (p.label_out) {
           unsigned int o = (unsigned)lab;
-          if (has_bg && bgs[(ty + 16 * r) * kB + tx] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+          if (has_bg && bgs[(ty + RSTEP * r) * kB + tx] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
           p.label_out[pix] = (uint8_t)o;
         }
       }
