@@ -8,6 +8,10 @@ Host-side mirror of the reference's Python surface for that path (SURVEY.md sect
   stitch    big-mask canvas fusion (segmentation_test.py:141-215), OEEM CAM ensemble
   mosaic    mosaic plan generator + synthesis (create_dataset.ipynb CropAndConcatDataset)
   dist      tile sharding + confusion-matrix all-reduce
+  validation  Lightning validation hooks (models/mosaic_module.py, models/segmentation_module.py) as a mixin
+  background  get_background (utils.py:155-163, dataset.py:100-109)
+  oeem      OEEM tiling positions, CAM ensemble exports (OEEM/classification/prepare_seg_inputs.py, generate_CAM.py)
+  io        palette PNG / .pt writers on a thread pool
 The compute lives in libpistoseg_b200.so; there is no CPU or torch fallback.
 """
 __version__ = "0.1.0"

@@ -505,7 +505,7 @@ __device__ __forceinline__ float filter_prepass(const FilterGeom& g, const uint3
       int dqa[K], dqb[K];
 #pragma unroll
       for (int q = 0; q < K; q++) { dqa[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[va]; dqb[q] = (cls[q + 1] - cls[0]) * g.plane_bytes[vc]; }
-#pragma unroll 2
+#pragma unroll 4
       for (int idx = tid; idx < cells; idx += nt) {
         const int i = (int)__umulhi((unsigned)idx, inv), j = idx - i * wo;
         const uint32_t aa = basea + i * ra + j * ca, ab = baseb + i * rb + j * cb;
