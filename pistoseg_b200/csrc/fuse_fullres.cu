@@ -394,6 +394,7 @@ static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t s
   pl.inv_nbx = (unsigned int)(((1ull << 32) + pl.nbx - 1) / pl.nbx);
   const long long items = (long long)p.N * pl.nby * pl.nbx;
   if (items > 0x7fffffffLL / 2) return PISTO_OK;
+  if ((long long)pl.nby * pl.nbx > 65535) return PISTO_OK;  // block index / nbx through the 32-bit inverse is exact below 2^16
   const int grid = (int)(items < h->sm_count ? items : h->sm_count);
   PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fuse_fullres_pipe_kernel<C, V><<<grid, kPThreads, smem, st>>>(p, pl);

@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, 4) mosaic_kernel(const __grid_consta
     const int sh = plan->split_h, sw = plan->split_w;
     const unsigned int inv_gpr = (unsigned int)((0x100000000ull + groups_per_row - 1) / groups_per_row);  // groups_per_row > 1
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-      const int Y = groups_per_row > 1 ? (int)__umulhi((unsigned)it, inv_gpr) : it, gx = it - Y * groups_per_row;
+      // it / groups_per_row through the 32-bit inverse is exact for it < 2^16 (S <= 512); larger mosaics take the division
+      const int Y = (groups_per_row > 1 && items <= 65536) ? (int)__umulhi((unsigned)it, inv_gpr) : it / groups_per_row, gx = it - Y * groups_per_row;
       unsigned int rgb[4], mask_bytes[4];
       // one output pixel, every case (the body used for groups that straddle the vertical split and for the rare slow taps)
       auto pixel = [&](int k, int q, const pisto_mosaic_quad_t* qd, int yc, int xc) {

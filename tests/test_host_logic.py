@@ -128,3 +128,13 @@ def test_mosaic_planner_is_a_pure_function_of_seed_and_index():
     for k, (a, s, dx, dy) in enumerate([(12.5, 0.9, 0.01, 0.03), (-33.0, 1.15, -0.05, 0.0)]):
         ref = mosaic.invert_affine(mosaic.shift_scale_rotate_matrix(224, 224, a, s, dx, dy)).reshape(-1)
         assert ref.tobytes() == inv[k].tobytes()
+
+
+def test_division_by_32bit_inverse_is_exact_below_65536():
+    """The kernels replace x / d by umulhi(x, ceil(2^32 / d)) (fuse_filter.cuh g_inv, fuse_fullres.cu fastdiv, mosaic.cu inv_gpr)
+    and guard the call sites to x < 2^16: the identity must hold for every such x and every divisor they can meet."""
+    import numpy as np
+    x = np.arange(65536, dtype=np.uint64)
+    for d in list(range(2, 300)) + [448, 512, 1000, 2047, 4096, 65535]:
+        inv = np.uint64(((1 << 32) + d - 1) // d)
+        assert np.array_equal((x * inv) >> np.uint64(32), x // np.uint64(d)), d
