@@ -10,6 +10,29 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Unmasked fast decision of one pixel (no present vector / MASK_NONE): the same test as pisto_decide -- best class leads the
+// runner-up by more than margin_abs + 2.4e-7 |best|, every score finite and below 1e30 -- written with min / max only (top-2
+// of C values in 3 (C - 1) FMNMX) and without the per-class presence selects.  Returns the label, or -1 when the pixel has to
+// take the exact path (near ties, exact ties, NaN / Inf, absurd magnitudes).
+template <int C>
+__device__ __forceinline__ int identity_decide_fast(const float (&a)[C], const DecideCfg& cfg) {
+  float bv = a[0], sv = -INFINITY, probe = a[0];
+#pragma unroll
+  for (int c = 1; c < C; c++) {
+    const float lo = fminf(bv, a[c]);
+    bv = fmaxf(bv, a[c]);
+    sv = fmaxf(sv, lo);
+    probe = __fadd_rn(probe, a[c]);
+  }
+  int bi = 0;
+#pragma unroll
+  for (int c = C - 1; c >= 1; c--) bi = (a[c] == bv) ? c : bi;
+  bi = (a[0] == bv) ? 0 : bi;
+  const float margin = __fmaf_rn(fabsf(bv), 2.4e-7f, cfg.margin_abs);
+  const bool ok = (__fsub_rn(bv, sv) > margin) && (fabsf(probe) < 1e30f) && (bv > -1e9f);   // NaN fails |probe| < 1e30
+  return ok ? bi : -1;
+}
+
 template <int C>
 __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_constant__ FuseParams p) {
   constexpr int BINS = C * C;
@@ -35,7 +58,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
     }
     lo = hi = 0; pending = 0;
   };
-  // all lanes of a warp run the same number of iterations (flush uses full-mask warp reductions)
+  const bool unmasked = !(p.present && p.dec.mask_mode != PISTO_MASK_NONE) && p.dec.mask_mode != PISTO_MASK_MULTIPLY;
   const long long warp_base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
   // (tile, group inside the tile) of the lane's current 4-pixel group, advanced without 64-bit divisions
   const long long q0 = warp_base + (threadIdx.x & 31);
@@ -45,6 +68,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
   const long long step_r = stride - (long long)step_n * q_per_tile;
   for (long long qb = warp_base; qb < total; qb += stride) {
     const long long q = qb + (threadIdx.x & 31);
+    unsigned int g4 = 0xffffffffu, l4 = 0;   // a dead lane contributes ground truth 255: never counted
     if (q < total) {
       const long long r4 = rq * 4;   // first pixel of the group inside the tile
       const TilePresence tp = pisto_tile_presence(p, n);
@@ -56,39 +80,26 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         float4 v[C];
 #pragma unroll
         for (int c = 0; c < C; c++) v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
-        float a[C];
+        float a[4][C];
 #pragma unroll
-        for (int c = 0; c < C; c++) a[c] = v[c].x;
-        lab[0] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+        for (int c = 0; c < C; c++) { a[0][c] = v[c].x; a[1][c] = v[c].y; a[2][c] = v[c].z; a[3][c] = v[c].w; }
+        bool all_ok = false;
+        if (unmasked) {
 #pragma unroll
-        for (int c = 0; c < C; c++) a[c] = v[c].y;
-        lab[1] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+          for (int j = 0; j < 4; j++) lab[j] = identity_decide_fast<C>(a[j], p.dec);
+          all_ok = (lab[0] | lab[1] | lab[2] | lab[3]) >= 0;
+        }
+        if (!all_ok) {
 #pragma unroll
-        for (int c = 0; c < C; c++) a[c] = v[c].z;
-        lab[2] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
-#pragma unroll
-        for (int c = 0; c < C; c++) a[c] = v[c].w;
-        lab[3] = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
-      }
-      const long long pix = (long long)n * hw + r4;
-      if (do_conf) {
-        const unsigned int g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const unsigned int gg = (g4 >> (8 * j)) & 0xffu;
-          if (gg < (unsigned)C) {
-            const unsigned int bn = gg * C + lab[j];
-            if (C <= 4) {
-              const unsigned long long inc = 1ull << (8 * (bn & 7));
-              if (bn < 8) lo += inc; else hi += inc;
-            } else {
-              atomicAdd(&hist[bn], 1u);
-            }
-          }
+          for (int j = 0; j < 4; j++)
+            if (!unmasked || lab[j] < 0) lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
         }
       }
+      const long long pix = (long long)n * hw + r4;
+      l4 = (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+      if (do_conf) g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
       if (p.label_out) {
-        unsigned int o = (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+        unsigned int o = l4;
         if (p.bg) {
           const unsigned int eq = __vcmpeq4(__ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix)), 0x01010101u * (unsigned)p.bg_match);
           o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
@@ -96,10 +107,25 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
       }
     }
-    n += step_n; rq += step_r;
-    if (rq >= q_per_tile) { rq -= q_per_tile; n++; }
+    if (do_conf && q < total) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned int gg = (g4 >> (8 * j)) & 0xffu;
+        if (gg < (unsigned)C) {
+          const unsigned int bn = gg * C + ((l4 >> (8 * j)) & 0xffu);
+          if (C <= 4) {
+            const unsigned long long inc = 1ull << (8 * (bn & 7));
+            if (bn < 8) lo += inc; else hi += inc;
+          } else {
+            atomicAdd(&hist[bn], 1u);
+          }
+        }
+      }
+    }
     pending += 4;
     if (do_conf && pending > 255 - 4) flush();
+    n += step_n; rq += step_r;
+    if (rq >= q_per_tile) { rq -= q_per_tile; n++; }
   }
   if (do_conf) {
     flush();
