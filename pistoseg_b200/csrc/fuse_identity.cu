@@ -45,18 +45,24 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
   const long long q_per_tile = hw / 4;
   const long long total = q_per_tile * p.N;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  unsigned long long lo = 0, hi = 0;  // packed 8-bit counters (C <= 4), flushed before they can overflow
+  // packed 8-bit counters (C <= 4): one 32-bit register per ground-truth class, byte l = predictions of class l; flushed before
+  // a byte can overflow
+  unsigned int rowcnt[C <= 4 ? C : 1];
+#pragma unroll
+  for (int i = 0; i < (C <= 4 ? C : 1); i++) rowcnt[i] = 0;
   int pending = 0;
   auto flush = [&]() {
     if (C <= 4) {
 #pragma unroll
       for (int b = 0; b < (C <= 4 ? BINS : 1); b++) {
-        unsigned int v = (unsigned int)(((b < 8 ? lo : hi) >> (8 * (b & 7))) & 0xffull);
+        unsigned int v = (rowcnt[C <= 4 ? b / C : 0] >> (8 * (b % C))) & 0xffu;
         v = __reduce_add_sync(0xffffffffu, v);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&hist[b], v);
       }
+#pragma unroll
+      for (int i = 0; i < (C <= 4 ? C : 1); i++) rowcnt[i] = 0;
     }
-    lo = hi = 0; pending = 0;
+    pending = 0;
   };
   const bool unmasked = !(p.present && p.dec.mask_mode != PISTO_MASK_NONE) && p.dec.mask_mode != PISTO_MASK_MULTIPLY;
   const long long warp_base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
@@ -110,15 +116,13 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
     if (do_conf && q < total) {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const unsigned int gg = (g4 >> (8 * j)) & 0xffu;
-        if (gg < (unsigned)C) {
-          const unsigned int bn = gg * C + ((l4 >> (8 * j)) & 0xffu);
-          if (C <= 4) {
-            const unsigned long long inc = 1ull << (8 * (bn & 7));
-            if (bn < 8) lo += inc; else hi += inc;
-          } else {
-            atomicAdd(&hist[bn], 1u);
-          }
+        const unsigned int gg = (g4 >> (8 * j)) & 0xffu, lb = (l4 >> (8 * j)) & 0xffu;
+        if (C <= 4) {
+          const unsigned int inc = 1u << (8 * lb);
+#pragma unroll
+          for (int c = 0; c < (C <= 4 ? C : 1); c++) rowcnt[c] += (gg == (unsigned)c) ? inc : 0u;
+        } else if (gg < (unsigned)C) {
+          atomicAdd(&hist[gg * C + lb], 1u);
         }
       }
     }
