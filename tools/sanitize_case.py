@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Small invocations of every hot kernel for compute-sanitizer (memcheck / racecheck): few tiles, all code paths."""
+"""Small invocations of every hot kernel (few tiles, all code paths, every CTA takes more than one tile): the input of a
+compute-sanitizer memcheck / racecheck run where the tool is available (it is closed on the build pool), and a quick
+"does every path still launch" check otherwise.  usage: sanitize_case.py [cfg2|cfg1|cfg3|cfg5|modef|all]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
