@@ -20,7 +20,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kB = 32;        // block side
 constexpr int kPad = kB + 1;  // shared-memory row pitch (floats)
-constexpr int kPT = kB + 4;   // pipelined kernel, transposing views: 16-byte aligned rows, column reads hit 8 banks (4-way conflict)
 
 template <int C>
 __global__ void __launch_bounds__(kThreads) fuse_fullres_kernel(const __grid_constant__ FuseParams p, int nby, int nbx, int n_transposed) {
@@ -182,14 +181,17 @@ struct ItemPos {
   }
 };
 
-template <int C, int V>
+// BH: output rows per block (32, or 16 when V * C planes of a 32 x 32 block do not fit twice: C = 4 with the 8 d4 views)
+template <int C, int V, int BH>
 __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ FullresPlan pl) {
   extern __shared__ __align__(16) float stage_mem[];  // [2][stage_floats]
   __shared__ unsigned int hist[C * C];
   constexpr int BINS = C * C;
-  constexpr int VPAR = kPThreads / 256;     // copy teams of 256 threads: team t issues the copies of views t, t + VPAR, ...
+  constexpr int TEAM = 8 * BH;              // 16-byte chunks per plane of a block = threads of a copy team
+  constexpr int VPAR = kPThreads / TEAM;    // team t issues the copies of views t, t + VPAR, ...
+  constexpr int PT = BH + 4;                // row pitch of a transposing view's tile (32 rows of BH source columns)
   constexpr int VH = (V + VPAR - 1) / VPAR;
-  constexpr int RPT = kB * kB / kPThreads;  // output rows per thread
+  constexpr int RPT = BH * kB / kPThreads;  // output rows per thread
   constexpr int RSTEP = kPThreads / 32;     // rows between a thread's output rows
   const bool do_conf = p.conf != nullptr && p.gt != nullptr;
   const bool has_bg = p.bg != nullptr && p.label_out != nullptr;
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   // view is the source row of output row y0 + r; tile row r of a transposing view is the source row of output COLUMN x0 + r.
   // Either way the tile holds 32 consecutive source columns as they lie in memory.
   // element offset of the thread's chunk inside a tile = koff + by * kdy + bx * kdx
-  const int cr = (tid >> 3) & 31, cq = tid & 7, vpar = tid >> 8;
+  const int cid = tid % TEAM, vpar = tid / TEAM;
+  const int cr = cid >> 3, cq = cid & 7;                  // row-preserving view: (tile row, chunk) of the thread's copy
+  const int tr = cid / (BH / 4), tq = cid % (BH / 4);     // transposing view: 32 tile rows of BH / 4 chunks
   int koff[VH], kdy[VH], kdx[VH], planes[VH];
 #pragma unroll
   for (int j = 0; j < VH; j++) {
@@ -216,11 +220,11 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
     planes[j] = vw.h * vw.w;
     if (m.ai != 0) {
       koff[j] = (m.a0 + cr * m.ai) * vw.w + (m.bj > 0 ? m.b0 : m.b0 - (kB - 1)) + 4 * cq;
-      kdy[j] = kB * m.ai * vw.w;
+      kdy[j] = BH * m.ai * vw.w;
       kdx[j] = m.bj > 0 ? kB : -kB;
     } else {
-      koff[j] = (m.a0 + cr * m.aj) * vw.w + (m.bi > 0 ? m.b0 : m.b0 - (kB - 1)) + 4 * cq;
-      kdy[j] = m.bi > 0 ? kB : -kB;
+      koff[j] = (m.a0 + tr * m.aj) * vw.w + (m.bi > 0 ? m.b0 : m.b0 - (BH - 1)) + 4 * tq;
+      kdy[j] = m.bi > 0 ? BH : -BH;
       kdx[j] = kB * m.aj * vw.w;
     }
   }
@@ -232,9 +236,9 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   auto issue = [&](const ItemPos& ip, int s, const TilePresence& tp) {
     const int n = ip.n;
     const int by = fastdiv(ip.rem, pl.nbx, pl.inv_nbx), bx = ip.rem - by * pl.nbx;
-    const int y0 = by * kB, x0 = bx * kB;
+    const int y0 = by * BH, x0 = bx * kB;
     const uint32_t sbase = smem0 + 4u * (uint32_t)(s * pl.stage_floats);
-    const bool full = y0 + kB <= T_h && x0 + kB <= T_w;
+    const bool full = y0 + BH <= T_h && x0 + kB <= T_w;
     if (vpar == 0 && y0 + cr < T_h && x0 + 4 * cq < T_w) {  // byte masks: 32 rows x 32 bytes, one 4-byte chunk per thread
       const long long o = (long long)n * hw + (long long)(y0 + cr) * T_w + x0 + 4 * cq;
       if (has_bg) cp_async4(sbase + 4u * (uint32_t)pl.bg_off + (uint32_t)(cr * kB + 4 * cq), p.bg + o);
@@ -247,19 +251,19 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
       if (v >= V) break;
       const ViewDev& vw = p.view[v];
       const ViewMap& m = vw.map;
-      const int pitch = m.ai != 0 ? kB : kPT;
       bool ok = true;
       if (!full) {
         int col;
         if (m.ai != 0) { col = (m.bj > 0 ? m.b0 + x0 : m.b0 - x0 - (kB - 1)) + 4 * cq; ok = y0 + cr < T_h; }
-        else { col = (m.bi > 0 ? m.b0 + y0 : m.b0 - y0 - (kB - 1)) + 4 * cq; ok = x0 + cr < T_w; }
+        else { col = (m.bi > 0 ? m.b0 + y0 : m.b0 - y0 - (BH - 1)) + 4 * tq; ok = x0 + tr < T_w; }
         ok = ok && col >= 0 && col + 3 < vw.w;
       }
       if (ok) {
         const float* g = vw.logits + (long long)n * vw.tile_stride + (koff[j] + by * kdy[j] + bx * kdx[j]);
-        const uint32_t d = sbase + 4u * (uint32_t)(pl.view_off[v] + cr * pitch + 4 * cq);
+        const uint32_t d = sbase + 4u * (uint32_t)(pl.view_off[v] + (m.ai != 0 ? cr * kB + 4 * cq : tr * PT + 4 * tq));
+        const int pfl = m.ai != 0 ? BH * kB : kB * PT;   // floats per class plane of the tile
 #pragma unroll
-        for (int c = 0; c < C; c++) cp_async16(d + 4u * (uint32_t)(c * kB * pitch), g + c * planes[j]);
+        for (int c = 0; c < C; c++) cp_async16(d + 4u * (uint32_t)(c * pfl), g + c * planes[j]);
       }
     }
   };
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
     __syncthreads();
     const int n = cur.n;
     const int by = fastdiv(cur.rem, pl.nbx, pl.inv_nbx), bx = cur.rem - by * pl.nbx;
-    const int y0 = by * kB, x0 = bx * kB;
+    const int y0 = by * BH, x0 = bx * kB;
     const TilePresence tp = tp_cur;
     const bool need_scores = tp.single < 0 || p.fused_out || need_low;
     const float* st = stage_mem + s * pl.stage_floats;
@@ -294,8 +298,8 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
         for (int r = 0; r < RPT; r++) {
           const int row = ty + RSTEP * r;
           int idx, cstride;
-          if (m.ai != 0) { idx = row * kB + (m.bj > 0 ? tx : kB - 1 - tx); cstride = kB * kB; }
-          else { idx = tx * kPT + (m.bi > 0 ? row : kB - 1 - row); cstride = kB * kPT; }  // 4-way bank conflict: negligible here
+          if (m.ai != 0) { idx = row * kB + (m.bj > 0 ? tx : kB - 1 - tx); cstride = BH * kB; }
+          else { idx = tx * PT + (m.bi > 0 ? row : BH - 1 - row); cstride = kB * PT; }  // 4-way bank conflict: negligible here
 #pragma unroll
           for (int c = 0; c < C; c++) {
             const float val = vb[idx + c * cstride];
@@ -365,8 +369,8 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   }
 }
 
-template <int C, int V>
-static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+template <int C, int V, int BH>
+static int launch_fullres_pipe_bh(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   static_assert(C <= 4, "packed 8-bit confusion counters");
   if (p.T_w % 4 || p.T_h > 65535 || p.T_w > 65535) return PISTO_OK;
   if ((((uintptr_t)p.bg | (uintptr_t)p.gt) & 3) || (((long long)p.T_h * p.T_w) % 4)) return PISTO_OK;  // 4-byte chunks of the byte masks
@@ -378,10 +382,10 @@ static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t s
     if (((uintptr_t)vw.logits & 15) || (vw.w % 4) || (vw.tile_stride % 4)) return PISTO_OK;  // 16-byte chunks
     if ((long long)vw.h * vw.w * 4 > 0x7fffffffLL / 8) return PISTO_OK;                      // 32-bit element offsets inside a tile
     pl.view_off[v] = fl;
-    fl += C * kB * (vw.map.ai != 0 ? kB : kPT);
+    fl += C * (vw.map.ai != 0 ? BH * kB : kB * (BH + 4));
   }
-  pl.bg_off = fl; fl += kB * kB / 4;
-  pl.gt_off = fl; fl += kB * kB / 4;
+  pl.bg_off = fl; fl += BH * kB / 4;
+  pl.gt_off = fl; fl += BH * kB / 4;
   pl.stage_floats = fl;
   if (p.low_fh > 0 && p.low_fw > 0) {
     pl.inv_fh = (unsigned int)(((1ull << 32) + p.low_fh - 1) / p.low_fh);
@@ -389,18 +393,27 @@ static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t s
   }
   const size_t smem = 2 * (size_t)fl * sizeof(float);
   if (smem > (size_t)h->smem_optin - 2048) return PISTO_OK;
-  pl.nby = (p.T_h + kB - 1) / kB;
+  pl.nby = (p.T_h + BH - 1) / BH;
   pl.nbx = (p.T_w + kB - 1) / kB;
   pl.inv_nbx = (unsigned int)(((1ull << 32) + pl.nbx - 1) / pl.nbx);
   const long long items = (long long)p.N * pl.nby * pl.nbx;
   if (items > 0x7fffffffLL / 2) return PISTO_OK;
   if ((long long)pl.nby * pl.nbx > 65535) return PISTO_OK;  // block index / nbx through the 32-bit inverse is exact below 2^16
   const int grid = (int)(items < h->sm_count ? items : h->sm_count);
-  PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fuse_fullres_pipe_kernel<C, V><<<grid, kPThreads, smem, st>>>(p, pl);
+  PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V, BH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fuse_fullres_pipe_kernel<C, V, BH><<<grid, kPThreads, smem, st>>>(p, pl);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   *launched = true;
+  return PISTO_OK;
+}
+
+// 32-row blocks when two stages of them fit, else 16-row blocks
+template <int C, int V>
+static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  int rc = launch_fullres_pipe_bh<C, V, 32>(h, p, st, launched);
+  if (rc != PISTO_OK || *launched) return rc;
+  if constexpr (kPThreads % (8 * 16) == 0 && 16 * kB >= kPThreads) return launch_fullres_pipe_bh<C, V, 16>(h, p, st, launched);
   return PISTO_OK;
 }
 
