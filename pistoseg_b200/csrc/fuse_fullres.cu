@@ -182,9 +182,10 @@ struct ItemPos {
 };
 
 // BH: output rows per block (32, or 16 when V * C planes of a 32 x 32 block do not fit twice: C = 4 with the 8 d4 views)
-template <int C, int V, int BH>
+// NS: stages of the cp.async ring (NS - 1 blocks in flight while one is summed)
+template <int C, int V, int BH, int NS>
 __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ FullresPlan pl) {
-  extern __shared__ __align__(16) float stage_mem[];  // [2][stage_floats]
+  extern __shared__ __align__(16) float stage_mem[];  // [NS][stage_floats]
   __shared__ unsigned int hist[C * C];
   constexpr int BINS = C * C;
   constexpr int TEAM = 8 * BH;              // 16-byte chunks per plane of a block = threads of a copy team
@@ -268,19 +269,28 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
     }
   };
 
-  ItemPos cur, nxt, nx2;
-  cur.n = (int)blockIdx.x / per_tile; cur.rem = (int)blockIdx.x - cur.n * per_tile;
-  nxt = cur; nxt.advance(step_n, step_rem, per_tile);
-  nx2 = nxt; nx2.advance(step_n, step_rem, per_tile);
-  TilePresence tp_cur = presence_of(cur), tp_next = presence_of(nxt);
-  if (cur.n < p.N) issue(cur, 0, tp_cur);
-  cp_async_commit();
-  int s = 0;
-  for (; cur.n < p.N; s ^= 1) {
-    const TilePresence tp_next2 = presence_of(nx2);  // requested two items ahead of its use
-    if (nxt.n < p.N) issue(nxt, s ^ 1, tp_next);
+  // ring of NS stages: items q[0] (being summed) .. q[NS-1] (the one issued in this iteration), q[NS] = the one whose presence
+  // vector is requested now, one iteration before its copies are issued
+  ItemPos q[NS + 1];
+  TilePresence tps[NS + 1];
+  q[0].n = (int)blockIdx.x / per_tile; q[0].rem = (int)blockIdx.x - q[0].n * per_tile;
+#pragma unroll
+  for (int j = 1; j <= NS; j++) { q[j] = q[j - 1]; q[j].advance(step_n, step_rem, per_tile); }
+#pragma unroll
+  for (int j = 0; j < NS; j++) tps[j] = presence_of(q[j]);
+#pragma unroll
+  for (int j = 0; j < NS - 1; j++) {
+    if (q[j].n < p.N) issue(q[j], j, tps[j]);
     cp_async_commit();
-    cp_async_wait<1>();   // this item's group has landed (the next item's may still be in flight)
+  }
+  int s = 0;
+  for (; q[0].n < p.N; s = (s + 1 == NS ? 0 : s + 1)) {
+    ItemPos& cur = q[0];
+    TilePresence& tp_cur = tps[0];
+    tps[NS] = presence_of(q[NS]);
+    if (q[NS - 1].n < p.N) issue(q[NS - 1], s == 0 ? NS - 1 : s - 1, tps[NS - 1]);
+    cp_async_commit();
+    cp_async_wait<NS - 1>();   // this item's group has landed (the NS - 1 younger ones may still be in flight)
     __syncthreads();
     const int n = cur.n;
     const int by = fastdiv(cur.rem, pl.nbx, pl.inv_nbx), bx = cur.rem - by * pl.nbx;
@@ -357,8 +367,9 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
         if (tx == 0 && v) atomicAdd(&hist[b], v);
       }
     }
-    tp_cur = tp_next; tp_next = tp_next2;
-    cur = nxt; nxt = nx2; nx2.advance(step_n, step_rem, per_tile);
+#pragma unroll
+    for (int j = 0; j < NS; j++) { q[j] = q[j + 1]; tps[j] = tps[j + 1]; }
+    q[NS].advance(step_n, step_rem, per_tile);
     __syncthreads();  // stage s is refilled two iterations from now, by copies issued after this barrier
   }
   cp_async_wait<0>();
@@ -369,7 +380,7 @@ __global__ void __launch_bounds__(kPThreads, 1) fuse_fullres_pipe_kernel(const _
   }
 }
 
-template <int C, int V, int BH>
+template <int C, int V, int BH, int NS>
 static int launch_fullres_pipe_bh(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   static_assert(C <= 4, "packed 8-bit confusion counters");
   if (p.T_w % 4 || p.T_h > 65535 || p.T_w > 65535) return PISTO_OK;
@@ -391,7 +402,7 @@ static int launch_fullres_pipe_bh(pisto_ctx* h, const FuseParams& p, cudaStream_
     pl.inv_fh = (unsigned int)(((1ull << 32) + p.low_fh - 1) / p.low_fh);
     pl.inv_fw = (unsigned int)(((1ull << 32) + p.low_fw - 1) / p.low_fw);
   }
-  const size_t smem = 2 * (size_t)fl * sizeof(float);
+  const size_t smem = NS * (size_t)fl * sizeof(float);
   if (smem > (size_t)h->smem_optin - 2048) return PISTO_OK;
   pl.nby = (p.T_h + BH - 1) / BH;
   pl.nbx = (p.T_w + kB - 1) / kB;
@@ -400,8 +411,8 @@ static int launch_fullres_pipe_bh(pisto_ctx* h, const FuseParams& p, cudaStream_
   if (items > 0x7fffffffLL / 2) return PISTO_OK;
   if ((long long)pl.nby * pl.nbx > 65535) return PISTO_OK;  // block index / nbx through the 32-bit inverse is exact below 2^16
   const int grid = (int)(items < h->sm_count ? items : h->sm_count);
-  PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V, BH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fuse_fullres_pipe_kernel<C, V, BH><<<grid, kPThreads, smem, st>>>(p, pl);
+  PISTO_CUDA(cudaFuncSetAttribute(fuse_fullres_pipe_kernel<C, V, BH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fuse_fullres_pipe_kernel<C, V, BH, NS><<<grid, kPThreads, smem, st>>>(p, pl);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
   *launched = true;
@@ -411,10 +422,13 @@ static int launch_fullres_pipe_bh(pisto_ctx* h, const FuseParams& p, cudaStream_
 // 32-row blocks when two stages of them fit, else 16-row blocks
 template <int C, int V>
 static int launch_fullres_pipe(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
-  int rc = launch_fullres_pipe_bh<C, V, 32>(h, p, st, launched);
+  // measured on Mode F (C = 3): 32-row blocks x 2 stages 0.80 M tiles/s; 16-row blocks x 3 / 4 stages 0.60 / 0.58 M (64-byte
+  // segments of the transposing views, one pixel per thread); C = 4: 16 rows x 2 stages 0.52 M, x 3 stages 0.51 M
+  static const bool deep = getenv("PISTO_FR_DEEP") != nullptr;  // A/B knob: 16-row blocks, 3 stages
+  if (deep) return launch_fullres_pipe_bh<C, V, 16, 3>(h, p, st, launched);
+  int rc = launch_fullres_pipe_bh<C, V, 32, 2>(h, p, st, launched);
   if (rc != PISTO_OK || *launched) return rc;
-  if constexpr (kPThreads % (8 * 16) == 0 && 16 * kB >= kPThreads) return launch_fullres_pipe_bh<C, V, 16>(h, p, st, launched);
-  return PISTO_OK;
+  return launch_fullres_pipe_bh<C, V, 16, 2>(h, p, st, launched);
 }
 
 template <int C>
