@@ -72,51 +72,64 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
   long long rq = q0 - (long long)n * q_per_tile;
   const int step_n = (int)(stride / q_per_tile);
   const long long step_r = stride - (long long)step_n * q_per_tile;
-  for (long long qb = warp_base; qb < total; qb += stride) {
-    const long long q = qb + (threadIdx.x & 31);
-    unsigned int g4 = 0xffffffffu, l4 = 0;   // a dead lane contributes ground truth 255: never counted
-    if (q < total) {
-      const long long r4 = rq * 4;   // first pixel of the group inside the tile
-      const TilePresence tp = pisto_tile_presence(p, n);
-      int lab[4];
-      if (tp.single >= 0) {
-        lab[0] = lab[1] = lab[2] = lab[3] = tp.single;
-      } else {
-        const float* base = vw.logits + (long long)n * vw.tile_stride + r4;
-        float4 v[C];
+  // Two groups (this grid-stride step's and the next one's) per iteration: all their loads are issued before the first is
+  // decided.  Since the unmasked decision became cheap the kernel is bound by the bytes a thread keeps in flight (60 registers
+  // -> 1024 threads per SM x 52 bytes was under the ~66 KB an SM needs outstanding to cover HBM latency at full rate).
+  struct Group { float4 v[C]; unsigned int g4, bg4; int n; long long r4; bool live, scores; TilePresence tp; };
+  auto fetch = [&](long long q_, int n_, long long rq_) {
+    Group gr;
+    gr.live = q_ < total; gr.n = n_; gr.r4 = rq_ * 4; gr.g4 = 0xffffffffu; gr.bg4 = 0; gr.scores = false;
+    gr.tp.bits = 0xffffffffu; gr.tp.single = -1;
+    if (gr.live) {
+      gr.tp = pisto_tile_presence(p, n_);
+      gr.scores = gr.tp.single < 0;
+      const long long pix = (long long)n_ * hw + gr.r4;
+      if (gr.scores) {
+        const float* base = vw.logits + (long long)n_ * vw.tile_stride + gr.r4;
 #pragma unroll
-        for (int c = 0; c < C; c++) v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
-        float a[4][C];
-#pragma unroll
-        for (int c = 0; c < C; c++) { a[0][c] = v[c].x; a[1][c] = v[c].y; a[2][c] = v[c].z; a[3][c] = v[c].w; }
-        bool all_ok = false;
-        if (unmasked) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) lab[j] = identity_decide_fast<C>(a[j], p.dec);
-          all_ok = (lab[0] | lab[1] | lab[2] | lab[3]) >= 0;
-        }
-        if (!all_ok) {
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (!unmasked || lab[j] < 0) lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
-        }
+        for (int c = 0; c < C; c++) gr.v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
       }
-      const long long pix = (long long)n * hw + r4;
-      l4 = (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
-      if (do_conf) g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
-      if (p.label_out) {
-        unsigned int o = l4;
-        if (p.bg) {
-          const unsigned int eq = __vcmpeq4(__ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix)), 0x01010101u * (unsigned)p.bg_match);
-          o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
-        }
-        *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
+      if (do_conf) gr.g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
+      if (p.label_out && p.bg) gr.bg4 = __ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix));
+    }
+    return gr;
+  };
+  auto process = [&](const Group& gr) {
+    if (!gr.live) return;
+    const TilePresence tp = gr.tp;
+    int lab[4];
+    if (!gr.scores) {
+      lab[0] = lab[1] = lab[2] = lab[3] = tp.single;
+    } else {
+      float a[4][C];
+#pragma unroll
+      for (int c = 0; c < C; c++) { a[0][c] = gr.v[c].x; a[1][c] = gr.v[c].y; a[2][c] = gr.v[c].z; a[3][c] = gr.v[c].w; }
+      bool all_ok = false;
+      if (unmasked) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) lab[j] = identity_decide_fast<C>(a[j], p.dec);
+        all_ok = (lab[0] | lab[1] | lab[2] | lab[3]) >= 0;
+      }
+      if (!all_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (!unmasked || lab[j] < 0) lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
       }
     }
-    if (do_conf && q < total) {
+    const long long pix = (long long)gr.n * hw + gr.r4;
+    const unsigned int l4 = (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+    if (p.label_out) {
+      unsigned int o = l4;
+      if (p.bg) {
+        const unsigned int eq = __vcmpeq4(gr.bg4, 0x01010101u * (unsigned)p.bg_match);
+        o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
+      }
+      *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
+    }
+    if (do_conf) {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const unsigned int gg = (g4 >> (8 * j)) & 0xffu, lb = (l4 >> (8 * j)) & 0xffu;
+        const unsigned int gg = (gr.g4 >> (8 * j)) & 0xffu, lb = (l4 >> (8 * j)) & 0xffu;
         if (C <= 4) {
           const unsigned int inc = 1u << (8 * lb);
 #pragma unroll
@@ -126,10 +139,20 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         }
       }
     }
-    pending += 4;
-    if (do_conf && pending > 255 - 4) flush();
+  };
+  // all lanes of a warp run the same number of iterations (flush uses full-mask warp reductions)
+  for (long long qb = warp_base; qb < total; qb += 2 * stride) {
+    const long long q = qb + (threadIdx.x & 31);
+    const Group ga = fetch(q, n, rq);
     n += step_n; rq += step_r;
     if (rq >= q_per_tile) { rq -= q_per_tile; n++; }
+    const Group gb = fetch(q + stride, n, rq);
+    n += step_n; rq += step_r;
+    if (rq >= q_per_tile) { rq -= q_per_tile; n++; }
+    process(ga);
+    process(gb);
+    pending += 8;
+    if (do_conf && pending > 255 - 8) flush();
   }
   if (do_conf) {
     flush();
