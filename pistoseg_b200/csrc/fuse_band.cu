@@ -17,7 +17,23 @@
 
 namespace {
 
-constexpr int kBThreads = 448;
+// Block shape (A/B knobs): threads per CTA, CTAs per SM, block width, rows per strip.  Two 256-thread CTAs per SM on 72 x 256
+// blocks let one CTA's pre-pass (global loads, latency-bound) and barriers overlap the other's row loop; one 448-thread CTA on
+// 72 x 512 blocks was the first version.
+#ifndef PISTO_BAND_THREADS
+#define PISTO_BAND_THREADS 256
+#endif
+#ifndef PISTO_BAND_CTAS
+#define PISTO_BAND_CTAS 2
+#endif
+#ifndef PISTO_BAND_BW
+#define PISTO_BAND_BW 256
+#endif
+#ifndef PISTO_BAND_RPS
+#define PISTO_BAND_RPS 18
+#endif
+constexpr int kBThreads = PISTO_BAND_THREADS;
+constexpr int kBCtas = PISTO_BAND_CTAS;
 
 struct BandGeom {
   int BH, BW, nby, nbx, S, GX;
@@ -50,7 +66,7 @@ __device__ __forceinline__ void exact_pixel_global(const FuseParams& p, const Fi
 
 // F: 1 bg, 2 gt/conf, 16 labels (compile-time feature mask as in fuse_filter.cuh; < 0: run-time)
 template <int C, int V, int G, int F>
-__global__ void __launch_bounds__(kBThreads, 1) fuse_band_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ FilterGeom g,
+__global__ void __launch_bounds__(kBThreads, kBCtas) fuse_band_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ FilterGeom g,
                                                                  const __grid_constant__ BandGeom bg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FCtl* ctl = reinterpret_cast<FCtl*>(smem_raw + bg.ctl_off);
@@ -338,12 +354,14 @@ int launch_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launch
   }
   if (Gn != G) return PISTO_OK;
   // block shape: 512 columns (4 per thread, 128 threads per row), 3 strips of 24 rows
-  b.BW = p.T_w < 512 ? p.T_w : 512;
+  b.BW = (p.T_w < PISTO_BAND_BW ? p.T_w : PISTO_BAND_BW) & ~31;   // the widest multiple of 32 up to the knob that divides the tile width
+  while (b.BW >= 32 && p.T_w % b.BW) b.BW -= 32;
+  if (b.BW < 32) return PISTO_OK;
   if (p.T_w % b.BW || b.BW % 32) return PISTO_OK;
   b.GX = b.BW / 4;
   b.S = (kBThreads / b.GX) < 8 ? (kBThreads / b.GX) : 8;
   if (b.S < 1) return PISTO_OK;
-  const int rps = 24;
+  const int rps = PISTO_BAND_RPS;
   b.BH = b.S * rps;
   if (b.BH > p.T_h) { b.BH = p.T_h; }
   for (int q = 0; q <= b.S; q++) b.strip_y0[q] = q * rps < b.BH ? q * rps : b.BH;
@@ -386,11 +404,12 @@ int launch_band(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launch
   b.queue_off = off; off += 4 * kFQueueCap;
   b.lab_off = off; off += b.BH * b.BW;
   b.smem_bytes = off;
-  if (off > h->smem_optin - 1024) return PISTO_OK;
+  if (off > (kBCtas > 1 ? (233472 / kBCtas - 1024) : h->smem_optin) - 1024) return PISTO_OK;
   auto kern = fuse_band_kernel<C, V, G, F>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b.smem_bytes));
   const long long items = (long long)p.N * b.nby * b.nbx;
-  const int grid = items < h->sm_count ? (int)items : h->sm_count;
+  const long long slots = (long long)h->sm_count * kBCtas;
+  const int grid = items < slots ? (int)items : (int)slots;
   const int threads = ((b.GX * b.S + 31) / 32) * 32;
   kern<<<grid, threads, b.smem_bytes, st>>>(p, g, b);
   h->launches++;
