@@ -1212,10 +1212,24 @@ int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   void (*kern)(FuseParams, FilterGeom);
   if constexpr (C >= 4) kern = fuse_filter_kernel_wide<C, V, G, F, NP, LSM, NB>;
   else kern = fuse_filter_kernel<C, V, G, F, NP, LSM, NB>;
+  // Small view sets (one or two stride-8 views: BASELINE config 1) leave more than half of the shared memory unused: two
+  // 256-thread CTAs per SM (the register file holds exactly 2 x 256 x 128) let one tile's vector pass -- global-memory
+  // latency -- overlap the other's row loop.  A/B knob: PISTO_FILTER_ONE_CTA.
+  int ctas = 1;
+  if constexpr (C < 4) {
+    static const bool one_cta = getenv("PISTO_FILTER_ONE_CTA") != nullptr;
+    FilterGeom g2;
+    if (!one_cta && 2 * (g.smem_bytes + 1024) <= 233472 && make_filter_geom(h, p, NP, G, LSM, NB, 256, filter_aux<F>(), &g2) &&
+        2 * (g2.smem_bytes + 1024) <= 233472 && g2.threads <= 256) {
+      g = g2;
+      ctas = 2;
+    }
+  }
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
-  const int grid = p.N < h->sm_count ? p.N : h->sm_count;
+  const int slots = h->sm_count * ctas;
+  const int grid = p.N < slots ? p.N : slots;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
