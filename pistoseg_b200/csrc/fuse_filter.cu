@@ -1,11 +1,16 @@
 // Dispatch of the filtered streaming fusion kernel (fuse_filter.cuh); the (C, V, G) families are instantiated in
 // fuse_filter_c3.cu / fuse_filter_c3b.cu / fuse_filter_c4.cu so that they compile in parallel.
+#include <stdlib.h>
+
 #include "fuse_common.cuh"
 
 int pisto_launch_filter_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched);
 int pisto_launch_filter_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched);
+int pisto_launch_static_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh
+int pisto_launch_static_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 
-// np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch)
+// np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch: the shape-specialised kernel of fuse_static.cuh
+// first), 3 = the shape-specialised kernel only
 int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   *launched = false;
   if (p.fuse_mode != PISTO_FUSE_LOGIT_MEAN) return PISTO_OK;       // softmax per view is not linear
@@ -15,6 +20,19 @@ int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st,
   if (p.T_h > 65535 || p.T_w > 65535) return PISTO_OK;
   const uintptr_t bytes = (uintptr_t)p.label_out | (uintptr_t)p.bg | (uintptr_t)p.gt;
   if (bytes & 1) return PISTO_OK;
+  bool views_aligned = true;
+  for (int v = 0; v < p.V; v++) views_aligned &= ((uintptr_t)p.view[v].logits & 15) == 0;  // TMA source spans need a 16-byte aligned allocation start
+  if ((np == 0 || np == 3) && views_aligned) {
+    static const bool no_static = getenv("PISTO_NO_STATIC") != nullptr;  // A/B knob
+    int rc = PISTO_OK;
+    // automatic dispatch: where it is measured faster than the generic kernel (C = 3, three scales x flip); always when asked for
+    if (np == 3 || (!no_static && p.C == 3 && p.V == 6)) {
+      if (p.C == 3) rc = pisto_launch_static_c3(h, p, st, launched);
+      else if (p.C == 4) rc = pisto_launch_static_c4(h, p, st, launched);
+    }
+    if (rc != PISTO_OK || *launched || np == 3) return rc;
+  }
+  if (np == 3) return PISTO_OK;
   if (np == 0) np = ((bytes & 3) == 0 && p.T_w % 4 == 0) ? 2 : 1;
   if (np == 2 && ((bytes & 3) || p.T_w % 4)) return PISTO_OK;
   for (int v = 0; v < p.V; v++)

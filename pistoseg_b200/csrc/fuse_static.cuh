@@ -1,0 +1,845 @@
+// Shape-specialised variant of the filtered fusion kernel (fuse_filter.cuh) for the WSSS4LUAD / BCSS production shape:
+// 224x224 tiles, stride-8 views of the scales {0.75, 1, 1.25} (21 / 28 / 35 px, each plain or with its hflip twin) or the single
+// 28 px view of BASELINE config 1, 32x32 logit export by the [3::7] gather (infer_pseudo_masks.py:118-154, loss.py:55-67).
+//
+// The algorithm, the error bound and every output are those of fuse_filter.cuh.  What changes is that the geometry is a
+// compile-time constant, so everything the generic kernel reads from shared-memory tables at run time is folded into the code:
+//
+//   row loop    224 = 7 strips x 32 rows, and 32 output rows cover exactly h/7 = 3 / 4 / 5 source rows of the three scale groups,
+//               so the schedule "which group's source-row pair moves down at which row" and the vertical weights are the SAME
+//               for every strip.  The 32 rows are fully unrolled: no row table, no flag tests, no branches; the vertical
+//               weight is an immediate operand of the packed fma (FFMA2 Rd, Ra, imm, Rc broadcasts a scalar immediate), map
+//               rows are addressed [base + imm].  The difference maps carry one replicated pad row above and below (like the
+//               two pad columns), so the top / bottom clamp of the bilinear index needs no special case: the two taps are
+//               equal there, Dh = 0, and the result is the clamped sample exactly.
+//   32x32       unit of work = (class, 4 low-resolution rows).  Source-row indices and vertical weights of a low-resolution
+//               row are compile-time constants, every source row a unit needs is interpolated horizontally ONCE (the generic
+//               kernel does it once per low-resolution row and class-plane address), taps are addressed [lane base + imm].
+//               The operation order per sample is unchanged (horizontal lerp, vertical lerp, sum in view order), so the
+//               export is still the reference's bit for bit.
+//
+// The weights are dyadic (h/224 = 3/32, 1/8, 5/32), so the constexpr tables equal pisto_src_index's float arithmetic exactly;
+// the host nevertheless re-derives every table entry with pisto_src_index before the first launch and refuses the kernel (the
+// caller falls back to the generic one) on any mismatch.
+#pragma once
+#include <type_traits>
+
+#include "fuse_filter.cuh"
+
+namespace {
+
+constexpr int kST = 224;    // tile side
+constexpr int kSGX = 56;    // threads per output row (4 columns each)
+constexpr int kSS = 7;      // strips
+constexpr int kSR = 32;     // rows per strip
+constexpr int kSLow = 32;   // low-resolution side of the logit export
+constexpr int kSCThreads = 416;  // 13 compute warps (392 workers)
+
+// compile-time loop with the index as a constant expression
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+__host__ __device__ constexpr int st_h(int G, int g) { return G == 1 ? 28 : (g == 0 ? 21 : (g == 1 ? 28 : 35)); }
+__host__ __device__ constexpr int st_floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+// output row r of a strip (0..31): unclamped lower source row relative to the strip's first one, in [-1, h/7 - 1], and the
+// weight of the upper row; src = (y + 0.5) h / 224 - 0.5 = ((2y + 1) h - 224) / 448 and 448 = 7 * 64, h = 7 * (h / 7)
+__host__ __device__ constexpr int st_i0rel(int h, int r) { return st_floordiv((2 * r + 1) * h - kST, 2 * kST); }
+__host__ __device__ constexpr float st_l1(int h, int r) { return (float)(((2 * r + 1) * h - kST - 2 * kST * st_i0rel(h, r)) / 7) * (1.f / 64.f); }
+__host__ __device__ constexpr bool st_adv(int h, int r) { return r > 0 && st_i0rel(h, r) != st_i0rel(h, r - 1); }
+// does the pair move at row rr of some / every block of U rows?
+__host__ __device__ constexpr bool st_adv_some(int h, int rr, int U) { bool s = false; for (int r = rr; r < 32; r += U) s = s || st_adv(h, r); return s; }
+__host__ __device__ constexpr bool st_adv_all(int h, int rr, int U) { bool s = true; for (int r = rr; r < 32; r += U) s = s && st_adv(h, r); return s; }
+// low-resolution row ly (0..31) = output row 7 ly + 3: src = ((2 ly + 1) h - 32) / 64, clamped as pisto_src_index does
+__host__ __device__ constexpr int lo_num(int h, int ly) { return (2 * ly + 1) * h - 32; }
+__host__ __device__ constexpr int lo_i0(int h, int ly) { return lo_num(h, ly) < 0 ? 0 : (lo_num(h, ly) / 64 > h - 1 ? h - 1 : lo_num(h, ly) / 64); }
+__host__ __device__ constexpr int lo_i1(int h, int ly) { return lo_i0(h, ly) + (lo_i0(h, ly) < h - 1 ? 1 : 0); }
+__host__ __device__ constexpr float lo_l1(int h, int ly) {
+  return lo_num(h, ly) < 0 ? 0.f : ((lo_num(h, ly) - 64 * lo_i0(h, ly)) >= 64 ? 1.f : (float)(lo_num(h, ly) - 64 * lo_i0(h, ly)) * (1.f / 64.f));
+}
+// byte offset of group g's difference maps inside the map area: (h + 2) x (h + 2) cells of KP floats each
+__host__ __device__ constexpr int st_ybytes(int G, int g, int KP) {
+  int off = 0;
+  for (int q = 0; q < g; q++) off += (4 * KP * (st_h(G, q) + 2) * (st_h(G, q) + 2) + 15) & ~15;
+  return off;
+}
+
+// shared-memory accesses at [register + immediate]
+template <int OFF> __device__ __forceinline__ float lds_f32_o(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ float2 lds_f2_o(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ float4 lds_f4_o(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_u32_o(uint32_t a, unsigned int v) { asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory"); }
+
+#ifndef PISTO_SU1
+#define PISTO_SU1 32
+#endif
+#ifndef PISTO_SU2
+#define PISTO_SU2 32
+#endif
+#ifndef PISTO_SNE
+#define PISTO_SNE 4
+#endif
+constexpr int kSU1 = PISTO_SU1;  // rows unrolled in the row loop for one difference field (32: the whole strip, every constant an immediate)
+constexpr int kSU2 = PISTO_SU2;  // ... for two / three fields (code size: the instruction caches hold ~32 KB)
+#ifndef PISTO_SAUX
+#define PISTO_SAUX 0
+#endif
+constexpr int kSAux = PISTO_SAUX;  // warps that only work on the 32x32 export
+constexpr int kSNE = PISTO_SNE;  // export units per class (each 32 / kSNE low-resolution rows)
+
+struct StaticGeom {
+  float wtab[kSR][4];                // -l0 of group g on row r of a strip (the unrolled-by-8 row loop reads it through uniform loads)
+  unsigned int adv[4];               // bit r of [g]: group g's source-row pair moves down at row r of a strip
+  int threads, cwarps, aux;
+  int view_off[PISTO_MAX_VIEWS];     // float offset of each view inside one staging buffer (16-byte aligned)
+  int vbase[PISTO_MAX_VIEWS], vcol[PISTO_MAX_VIEWS];  // byte address of de-augmented (i, j) inside a plane: vbase + 4 w i + j vcol
+  int buf_floats;
+  float tau_coef, tau_abs;
+  int ctl_off, col4_off, col4i_off, lowtab_off, ymap_off, queue_off, lab_off, views_off, smem_bytes;
+  int* counter;
+};
+
+// rows of the strip whose 4-pixel group failed the lead test -> one queue entry per group: (y << 16) | x (x is a multiple of 4;
+// the exact pass re-evaluates the 4 pixels of an entry, spread over all warps)
+__device__ __noinline__ void static_push_groups(FCtl* ctl, uint32_t* queue, int b, int ys, int x, unsigned int rows) {
+  while (rows) {
+    const int r = __ffs(rows) - 1;
+    rows &= rows - 1;
+    const unsigned int idx = atomicAdd(&ctl->qcount[b], 1u);
+    if (idx < (unsigned)kFQueueCap) queue[idx] = ((unsigned)(ys + r) << 16) | (unsigned)x;
+  }
+}
+
+// horizontally interpolated values of the thread's 4 columns on one map row (3 adjacent source cells at `a`)
+template <int K, int OFF>
+__device__ __forceinline__ void static_load_h(uint32_t a, const float4 L1, unsigned int sel, u64 (&H)[K][2]) {
+  const u64 one2 = pack2(1.f, 1.f);
+  const u64 l1a = pack2(L1.x, L1.y), l1b = pack2(L1.z, L1.w);
+  const u64 l0a = sub2(one2, l1a), l0b = sub2(one2, l1b);
+  const bool s1 = (sel >> 1) & 1u, s2 = (sel >> 2) & 1u, s3 = (sel >> 3) & 1u;
+  float y0[K], y1[K], y2[K];
+  if constexpr (K == 1) {
+    y0[0] = lds_f32_o<OFF>(a); y1[0] = lds_f32_o<OFF + 4>(a); y2[0] = lds_f32_o<OFF + 8>(a);
+  } else if constexpr (K == 2) {
+    const float2 v0 = lds_f2_o<OFF>(a), v1 = lds_f2_o<OFF + 8>(a), v2 = lds_f2_o<OFF + 16>(a);
+    y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+  } else {
+    const float4 v0 = lds_f4_o<OFF>(a), v1 = lds_f4_o<OFF + 16>(a), v2 = lds_f4_o<OFF + 32>(a);
+    y0[0] = v0.x; y0[1 % K] = v0.y; y0[K - 1] = v0.z; y1[0] = v1.x; y1[1 % K] = v1.y; y1[K - 1] = v1.z;
+    y2[0] = v2.x; y2[1 % K] = v2.y; y2[K - 1] = v2.z;
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const float a1 = s1 ? y1[k] : y0[k], b1 = s1 ? y2[k] : y1[k];
+    const float a2 = s2 ? y1[k] : y0[k], b2 = s2 ? y2[k] : y1[k];
+    const float a3 = s3 ? y1[k] : y0[k], b3 = s3 ? y2[k] : y1[k];
+    H[k][0] = fma2(l0a, pack2(y0[k], a1), mul2(l1a, pack2(y1[k], b1)));
+    H[k][1] = fma2(l0b, pack2(a2, a3), mul2(l1b, pack2(b2, b3)));
+  }
+}
+
+// ---- the 32 rows of one strip: blocks of U rows, each block fully unrolled -------------------------------------------------
+// U = 32: one block, every schedule decision and weight is a compile-time constant.  U = 8: four passes over the same code; a
+// refill site is unconditional when the group moves at that row of every block (h = 28), tested against a uniform bit mask
+// when it moves there in some blocks, and absent otherwise; the weights come from the parameter block (uniform loads, the
+// packed fma takes a uniform-register operand).
+// col4_t: address of the thread's float4 {l1 of its 4 columns} (group stride 16 * 56); col4i_t: address of its
+// (bytes-per-float * j0 | sel << 16) word (group stride 4 * 56); lab_a: label-tile address of (first row of the strip, x)
+template <int G, int K, int U>
+// Returns the rows of the strip (bit r) on which the thread's 4-pixel group failed the lead test.
+__device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_t col4_t, uint32_t col4i_t, uint32_t ymap_s, uint32_t lab_a, int strip,
+                                                    const unsigned int (&c4)[4], float tau) {
+  constexpr int KP = K == 3 ? 4 : K;
+  constexpr int NBLK = kSR / U;
+  static_assert(U == 32 || U == 16 || U == 8 || U == 4, "row-loop unroll: 4, 8, 16 or 32");
+  u64 Hb[G][K][2], Dh[G][K][2], base[K][2];
+  uint32_t yb[G];  // address of the map row that holds Ha (cell of the thread's first column)
+  unsigned int selm[G];
+  constexpr bool HOIST = K == 1;  // the horizontal weights of the thread's columns stay in registers (else: one 16-byte load per refill)
+  float4 L1[G] = {};
+  auto l1_of = [&](int gi) { return HOIST ? L1[gi] : lds_f4(col4_t + gi * 16u * kSGX); };
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+    const uint32_t u = lds_u32(col4i_t + gi * 4u * kSGX);
+    // row (in the padded map) of Ha on output row 0 of the strip: strip * h/7 + i0rel(0) + 1
+    yb[gi] = ymap_s + st_ybytes(G, gi, KP) + KP * (u & 0xffffu) + (uint32_t)(strip * (h / 7) + st_i0rel(h, 0) + 1) * RS;
+    selm[gi] = u >> 16;
+    L1[gi] = lds_f4(col4_t + gi * 16u * kSGX);
+    u64 Ha[K][2];
+    static_load_h<K, 0>(yb[gi], L1[gi], selm[gi], Ha);
+    static_load_h<K, RS>(yb[gi], L1[gi], selm[gi], Hb[gi]);
+    if (!HOIST) L1[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) Dh[gi][k][q] = sub2(Hb[gi][k][q], Ha[k][q]);
+  });
+  auto rebase = [&]() {
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        u64 s = Hb[0][k][q];
+#pragma unroll
+        for (int gi = 1; gi < G; gi++) s = add2(s, Hb[gi][k][q]);
+        base[k][q] = s;
+      }
+  };
+  rebase();
+  unsigned int unc_rows = 0;  // bit r: row r of the strip failed the lead test
+#pragma unroll 1
+  for (int blk = 0; blk < NBLK; blk++) {
+    unsigned int unc_blk = 0;
+    unsigned int advb[G];
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) advb[gi] = U == 32 ? 0u : g.adv[gi] >> (blk * U);
+    static_for<0, U>([&](auto RI) {
+      constexpr int rr = decltype(RI)::value;
+      bool moved = false;
+      static_for<0, G>([&](auto GI) {
+        constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+        constexpr bool some = st_adv_some(h, rr, U), all = st_adv_all(h, rr, U);
+        if constexpr (some) {
+          bool now = true;
+          if constexpr (!all) now = (advb[gi] >> rr) & 1u;
+          if (now) {
+            yb[gi] += RS;
+            u64 Hn[K][2];
+            static_load_h<K, RS>(yb[gi], l1_of(gi), selm[gi], Hn);
+#pragma unroll
+            for (int k = 0; k < K; k++)
+#pragma unroll
+              for (int q = 0; q < 2; q++) { Dh[gi][k][q] = sub2(Hn[k][q], Hb[gi][k][q]); Hb[gi][k][q] = Hn[k][q]; }
+            moved = true;
+          }
+        }
+      });
+      if (moved) rebase();
+      float w[G];
+      if constexpr (U == 32) {
+        static_for<0, G>([&](auto GI) { constexpr int gi = decltype(GI)::value; w[gi] = st_l1(st_h(G, gi), rr) - 1.f; });  // -l0
+      } else {
+        const float4 t = *reinterpret_cast<const float4*>(g.wtab[blk * U + rr]);
+        if (G > 2) w[G > 2 ? 2 : 0] = t.z;
+        if (G > 1) w[G > 1 ? 1 : 0] = t.y;
+        w[0] = t.x;
+      }
+      u64 acc[K][2];
+#pragma unroll
+      for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          u64 a = base[k][q];
+#pragma unroll
+          for (int gi = 0; gi < G; gi++) a = fma2(pack2(w[gi], w[gi]), Dh[gi][k][q], a);
+          acc[k][q] = a;
+        }
+      unsigned int lab4;
+      if (!labels_from_diffs<K, 2>(acc, c4, tau, lab4)) unc_blk |= 1u << rr;
+      sts_u32_o<rr * kST>(lab_a, lab4);
+    });
+    lab_a += U * kST;
+    unc_rows |= unc_blk << (blk * U);
+  }
+  return unc_rows;
+}
+
+// ---- pre-pass: Y[g][k] = sum over the views of group g of (x[c_{k+1}] - x[c_0]) in the de-augmented frame, maps padded by one
+// replicated row above / below and two replicated columns on the right; returns the thread's max |x| (NaN-propagating)
+template <int C, int G, int VPG, int K>
+__device__ __forceinline__ float static_prepass(const StaticGeom& g, const uint32_t (&vb)[G * VPG], const int (&cls)[C], uint32_t ymap_s, int tid, int nt) {
+  constexpr int KP = K == 3 ? 4 : K;
+  constexpr uint32_t ES = 4u * KP;
+  float mxf = 0.f;
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), PL = 4 * h * h, W2 = h + 2;
+    constexpr int va = gi * VPG, vc = gi * VPG + VPG - 1;
+    const uint32_t ym = ymap_s + st_ybytes(G, gi, KP);
+    const uint32_t basea = vb[va] + g.vbase[va] + cls[0] * PL, baseb = vb[vc] + g.vbase[vc] + cls[0] * PL;
+    const int ca = g.vcol[va], cb = g.vcol[vc];
+    int dq[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) dq[q] = (cls[q + 1] - cls[0]) * PL;
+#pragma unroll 2
+    for (int idx = tid; idx < h * h; idx += nt) {
+      const int i = idx / h, j = idx - i * h;
+      const uint32_t aa = basea + 4 * h * i + j * ca, ab = baseb + 4 * h * i + j * cb;
+      const float x0a = lds_f32(aa), x0b = VPG == 2 ? lds_f32(ab) : 0.f;
+      mxf = max_nan(mxf, fabsf(x0a));
+      if (VPG == 2) mxf = max_nan(mxf, fabsf(x0b));
+      const uint32_t ya = ym + ES * (uint32_t)((i + 1) * W2 + j);
+      const bool lastc = j == h - 1, top = i == 0, bot = i == h - 1;
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        const float xa = lds_f32(aa + dq[q]);
+        mxf = max_nan(mxf, fabsf(xa));
+        float yv = __fsub_rn(xa, x0a);
+        if (VPG == 2) {
+          const float xb = lds_f32(ab + dq[q]);
+          mxf = max_nan(mxf, fabsf(xb));
+          yv = __fadd_rn(yv, __fsub_rn(xb, x0b));
+        }
+        const uint32_t yq = ya + 4u * q;
+        sts_f32(yq, yv);
+        if (lastc | top | bot) {
+          if (lastc) { sts_f32(yq + ES, yv); sts_f32(yq + 2u * ES, yv); }
+          if (top | bot) {
+            const uint32_t yp = top ? yq - ES * W2 : yq + ES * W2;
+            sts_f32(yp, yv);
+            if (lastc) { sts_f32(yp + ES, yv); sts_f32(yp + 2u * ES, yv); }
+          }
+        }
+      }
+    }
+  });
+  return mxf;
+}
+
+// a / V for the export (pisto_div_views with the IEEE division out of line: the unit code is replicated per row group)
+__device__ __noinline__ float static_div_slow(float a, float fV) { return __fdiv_rn(a, fV); }
+__device__ __forceinline__ float static_div_views(float a, const DecideCfg& cfg) {
+  // V = 1 and powers of two: rcp_v is exact, e = 0, r = q -- the same quotient pisto_div_views returns on its short cuts
+  const float q = __fmul_rn(a, cfg.rcp_v);
+  const float e = __fmaf_rn(-cfg.fV, q, a);
+  const float r = __fmaf_rn(e, cfg.rcp_v, q);
+  const float fa = fabsf(a);
+  if (fa > 1e-30f && fa < 1e30f) return r;
+  return static_div_slow(a, cfg.fV);
+}
+
+// ---- 32x32 logit export: unit (class c, low-resolution rows RPU E .. RPU E + RPU - 1), lane = low-resolution column.  sA / sB:
+// shared-memory address of the lane's left / right tap in row 0 of class 0 of each view.  The views of a group (a scale and its
+// flipped twin) share every constant, so they run through the same code (a two-trip loop); the sum starts from -0.f, the
+// identity of IEEE addition, so that the first view needs no special case.
+template <int C, int G, int VPG, int RPU, int E>
+__device__ __forceinline__ void static_export_unit(const FuseParams& p, int n, int c, const uint32_t (&sA)[G * VPG], const uint32_t (&sB)[G * VPG],
+                                                   const float (&lx0)[G], const float (&lx1)[G]) {
+  float a[RPU];
+#pragma unroll
+  for (int r = 0; r < RPU; r++) a[r] = -0.f;
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), PL = 4 * h * h, RB = 4 * h;
+    constexpr int imin = lo_i0(h, RPU * E), imax = lo_i1(h, RPU * E + RPU - 1);
+#pragma unroll 1
+    for (int tw = 0; tw < VPG; tw++) {
+      const uint32_t b0 = (tw ? sA[gi * VPG + VPG - 1] : sA[gi * VPG]) + (uint32_t)(c * PL);
+      const uint32_t b1 = (tw ? sB[gi * VPG + VPG - 1] : sB[gi * VPG]) + (uint32_t)(c * PL);
+      float Hr[imax - imin + 1];
+      static_for<imin, imax + 1>([&](auto II) {
+        constexpr int i = decltype(II)::value;
+        Hr[i - imin] = __fmaf_rn(lx0[gi], lds_f32_o<i * RB>(b0), __fmul_rn(lx1[gi], lds_f32_o<i * RB>(b1)));
+      });
+      static_for<0, RPU>([&](auto RI) {
+        constexpr int r = decltype(RI)::value, ly = RPU * E + r;
+        constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
+        const float u = __fmaf_rn(l0, Hr[lo_i0(h, ly) - imin], __fmul_rn(l1, Hr[lo_i1(h, ly) - imin]));
+        a[r] = __fadd_rn(a[r], u);
+      });
+    }
+  });
+  float* outp = p.lowres_out + ((long long)(n * C + c) * kSLow + RPU * E) * kSLow + (threadIdx.x & 31);
+#pragma unroll
+  for (int r = 0; r < RPU; r++) outp[r * kSLow] = static_div_views(a[r], p.dec);
+}
+
+template <int C, int G, int VPG, int F, int NB>
+__global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ StaticGeom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int V = G * VPG;
+  constexpr bool RT = F < 0;
+  FCtl* ctl = reinterpret_cast<FCtl*>(smem_raw + g.ctl_off);
+  float4* col4 = reinterpret_cast<float4*>(smem_raw + g.col4_off);        // [G][56] l1 of the thread's 4 columns
+  uint32_t* col4i = reinterpret_cast<uint32_t*>(smem_raw + g.col4i_off);  // [G][56] (4 * j0 of column 0) | sel << 16
+  uint2* lowtap = reinterpret_cast<uint2*>(smem_raw + g.lowtab_off);      // [32 lanes][V] byte offsets of the left / right tap of low-res column `lane`
+  float2* lowwt = reinterpret_cast<float2*>(smem_raw + g.lowtab_off + 32 * 8 * V);  // [32][G] {l0, l1}
+  float* ymap = reinterpret_cast<float*>(smem_raw + g.ymap_off);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + g.queue_off);
+  uint8_t* labsm = smem_raw + g.lab_off;
+  float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
+  const bool do_conf = RT ? (p.conf != nullptr && p.gt != nullptr) : ((F & 2) != 0);
+  const bool need_low = NB == 2 && (RT ? (p.lowres_out != nullptr && p.low_fh > 0) : ((F & 8) != 0));
+  const bool has_label = RT ? (p.label_out != nullptr) : ((F & 16) != 0);
+  constexpr int BINS = C * C;
+  constexpr int UNITS = C * kSNE;  // export units per tile
+
+  if (tid == 0) {
+    mbar_init(&ctl->full[0], 1);
+    mbar_init(&ctl->full[1], 1);
+    mbar_init(&ctl->empty[0], g.cwarps + (need_low ? g.aux : 0));
+    mbar_init(&ctl->empty[1], g.cwarps + (need_low ? g.aux : 0));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ctl->maxbits[0] = ctl->maxbits[1] = 0u;
+    ctl->lownext[0] = ctl->lownext[1] = 0u;
+    ctl->qcount[0] = ctl->qcount[1] = 0u;
+  }
+  for (int i = tid; i < 64; i += nthreads) ctl->hist[i] = 0;
+  for (int i = tid; i < G * kSGX; i += nthreads) {
+    const int gi = i / kSGX, gx = i - gi * kSGX;
+    const int h = gi == 0 ? st_h(G, 0) : (gi == 1 ? st_h(G, G > 1 ? 1 : 0) : st_h(G, G > 2 ? 2 : 0));
+    const float sc = (float)h / (float)kST;
+    Lerp L[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) L[c] = pisto_src_index(sc, 4 * gx + c, h, false);
+    col4[i] = make_float4(L[0].l1, L[1].l1, L[2].l1, L[3].l1);
+    unsigned int sel = 0;
+#pragma unroll
+    for (int c = 1; c < 4; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;  // 0 or 1 (checked on the host)
+    col4i[i] = (unsigned)(4 * L[0].i0) | (sel << 16);
+  }
+
+  if (need_low && tid < 32) {
+    static_for<0, V>([&](auto VI) {
+      constexpr int v = decltype(VI)::value, gi = v / VPG, h = st_h(G, gi);
+      const Lerp L = pisto_src_index((float)h / (float)kST, 7 * tid + 3, h, false);
+      lowtap[tid * V + v] = make_uint2((uint32_t)(g.vbase[v] + L.i0 * g.vcol[v]), (uint32_t)(g.vbase[v] + L.i1 * g.vcol[v]));
+      lowwt[tid * G + gi] = make_float2(L.l0, L.l1);
+    });
+  }
+
+  auto issue_tile = [&](int n, int b) {
+    float* buf = vsm + b * g.buf_floats;
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      const char* start = reinterpret_cast<const char*>(vw.logits + (long long)n * vw.tile_stride);
+      const char* end = start + (size_t)C * vw.h * vw.w * sizeof(float);
+      const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15);
+      const char* a1 = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(end) + 15) & ~(uintptr_t)15);
+      char* dst = reinterpret_cast<char*>(buf + g.view_off[v]);
+      if (n == p.N - 1) {  // never read past the end of the caller's buffer: whole 16-byte units only, the tail by hand
+        a1 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(end) & ~(uintptr_t)15);
+        if (a1 < a0) a1 = a0;
+        const char* t = a1 > start ? a1 : start;
+        for (; t < end; t += 4) *reinterpret_cast<float*>(dst + (t - a0)) = *reinterpret_cast<const float*>(t);
+      }
+      const uint32_t bytes = (uint32_t)(a1 - a0);
+      if (bytes) bulk_g2s(dst, a0, bytes, &ctl->full[b]);
+      total += bytes;
+    }
+    mbar_arrive_expect_tx(&ctl->full[b], total);
+  };
+
+  __syncthreads();
+
+  const int ncomp = g.cwarps * 32;
+  if (tid >= ncomp + 32 * g.aux) {
+    // ===== producer warp
+    if (tid == ncomp + 32 * g.aux) {
+      const long long tile_px = (long long)kST * kST;
+      int next = atomicAdd(g.counter, 1);
+      TilePresence next_tp; next_tp.bits = 0u; next_tp.single = -1;
+      if (next < p.N) next_tp = pisto_tile_presence(p, next);
+      bool next_views = next < p.N && (need_low || next_tp.single < 0);
+      for (int k = 0;; k++) {
+        const int b = NB == 2 ? (k & 1) : 0;
+        if (k >= NB) mbar_wait_sleep(&ctl->empty[b], NB == 2 ? (((k >> 1) - 1) & 1) : ((k - 1) & 1));
+        const int tile = next < p.N ? next : -1;
+        ctl->tile[b] = tile;
+        ctl->pres_bits[b] = next_tp.bits;
+        ctl->pres_single[b] = next_tp.single;
+        ctl->lownext[b] = 0u;
+        if (tile >= 0 && next_views) issue_tile(tile, b);
+        else mbar_arrive(&ctl->full[b]);
+        if (tile < 0) break;
+        if (has_bg && ((uintptr_t)p.bg & 15) == 0) bulk_prefetch_l2(p.bg + tile * tile_px, (uint32_t)tile_px);
+        if (do_conf && ((uintptr_t)p.gt & 15) == 0) bulk_prefetch_l2(p.gt + tile * tile_px, (uint32_t)tile_px);
+        next = atomicAdd(g.counter, 1);
+        if (next < p.N) next_tp = pisto_tile_presence(p, next);
+        next_views = next < p.N && (need_low || next_tp.single < 0);
+      }
+    }
+    return;
+  }
+
+  // ---- 32x32 export: units claimed from a shared counter; lane = low-resolution column, its taps / weights come from a table
+  auto export_units = [&](int n, int b, const uint32_t (&vb)[V]) {
+    const int lane = tid & 31;
+    uint32_t sA[V], sB[V];
+    float lx0[G], lx1[G];
+#pragma unroll
+    for (int v = 0; v < V; v++) { const uint2 t = lowtap[lane * V + v]; sA[v] = vb[v] + t.x; sB[v] = vb[v] + t.y; }
+#pragma unroll
+    for (int q = 0; q < G; q++) { const float2 t = lowwt[lane * G + q]; lx0[q] = t.x; lx1[q] = t.y; }
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = (int)atomicAdd(&ctl->lownext[b], 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= UNITS) break;
+      const int c = u / kSNE, e = u - c * kSNE;
+      static_for<0, kSNE>([&](auto EI) {
+        constexpr int E = decltype(EI)::value;
+        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(p, n, c, sA, sB, lx0, lx1);
+      });
+    }
+  };
+
+  // ===== compute warps (tid < ncomp) and export warps: one tile loop; the export warps skip the label work and go straight to
+  // the 32x32 units, the compute warps join them when their own work on the tile is done (the unit code exists once)
+  const bool is_export = tid >= ncomp;
+  if (is_export && !need_low) return;
+  const int grp = tid % kSGX, strip = min(tid / kSGX, kSS - 1);
+  const bool worker = tid < kSGX * kSS;
+  const int x = 4 * grp;
+  const uint32_t ymap_s = smem_u32(ymap);
+  const uint32_t col4_t = smem_u32(col4) + 16u * grp, col4i_t = smem_u32(col4i) + 4u * grp;
+  const uint32_t lab_s = smem_u32(labsm);
+  const int nt = ncomp;
+  constexpr long long tpx = (long long)kST * kST;
+
+  for (int k = 0;; k++) {
+    const int b = k & 1;
+    const int sb = NB == 2 ? b : 0;
+    mbar_wait(&ctl->full[sb], NB == 2 ? ((k >> 1) & 1) : (k & 1));
+    const int n = ctl->tile[sb];
+    if (n < 0) break;
+    uint32_t vb[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+      vb[v] = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
+    }
+    if (!is_export) {
+    TilePresence tp = pisto_tile_presence(p, n);
+    if (p.present) { tp.bits = ctl->pres_bits[sb]; tp.single = ctl->pres_single[sb]; }
+    const bool multi = tp.single < 0;
+    int cls[C], P = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) cls[c] = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if ((tp.bits >> c) & 1u) {
+#pragma unroll
+        for (int q = 0; q < C; q++)
+          if (q == P) cls[q] = c;
+        P++;
+      }
+
+#ifdef PISTO_X_SKIP_PREPASS
+    if (false) {
+#else
+    if (multi && P >= 2) {
+#endif
+      float mxf;
+      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tid, nt);
+      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tid, nt);
+      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
+      if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
+    }
+    bar_sync(1, ncomp);
+    if (NB == 1 && (tid & 31) == 0) mbar_arrive(&ctl->empty[0]);
+    if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone
+
+    bool exact_all = false;
+    if (multi) {
+      float tau = 0.f;
+      if (P >= 2) {
+        const float A = __fmul_rn((float)V, __uint_as_float(ctl->maxbits[b]));
+        tau = __fmaf_rn(A, g.tau_coef, g.tau_abs);
+        if (!(A < 5e8f)) exact_all = true;
+      } else {
+        exact_all = true;
+      }
+      // one exact sample sum per class at (yy, xx), evaluated by the whole warp: lane l computes the bilinear sample of
+      // (view l / C, class l % C), the sums are then formed in view order through shuffles (the reference's operation order)
+      auto exact_warp = [&](int yy, int xx) {
+        const int lane = tid & 31;
+        float o = 0.f;
+        if (lane < V * C) {
+          const int v = lane / C, c = lane - v * C;
+          const ViewDev& vw = p.view[v];
+          const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, false);
+          const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, false);
+          const int pl = g.vbase[v] + c * 4 * vw.h * vw.w;
+          const int r0 = pl + Ly.i0 * 4 * vw.w, r1 = pl + Ly.i1 * 4 * vw.w;
+          const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+          float x00, x01, x10, x11;
+          if (NB == 2) {
+            const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+            const uint32_t base = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
+            x00 = lds_f32(base + r0 + c0); x01 = lds_f32(base + r0 + c1); x10 = lds_f32(base + r1 + c0); x11 = lds_f32(base + r1 + c1);
+          } else {  // single staging buffer: already released, read L2 / HBM
+            const float* gsrc = vw.logits + (long long)n * vw.tile_stride;
+            x00 = __ldg(gsrc + ((r0 + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + c1) >> 2));
+            x10 = __ldg(gsrc + ((r1 + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + c1) >> 2));
+          }
+          const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+          const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+          o = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+        }
+        float a[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          a[c] = __shfl_sync(0xffffffffu, o, c);
+#pragma unroll
+          for (int v = 1; v < V; v++) a[c] = __fadd_rn(a[c], __shfl_sync(0xffffffffu, o, (v * C + c) & 31));
+        }
+        const int lab = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+        if (lane == 0) labsm[yy * kST + xx] = (uint8_t)lab;
+      };
+      unsigned int unc = 0;
+#ifdef PISTO_X_SKIP_ROWS
+      if (false) {
+#else
+      if (!exact_all && worker) {
+#endif
+        unsigned int c4[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) c4[q] = 0x01010101u * (unsigned)cls[q < C ? q : 0];
+        const uint32_t lab_a = lab_s + (uint32_t)(strip * kSR * kST + x);
+        if (P == 2) unc = static_rows<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+        else if (P == 3) unc = static_rows<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+        else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+      }
+      if (unc) static_push_groups(ctl, queue, b, strip * kSR, x, unc);
+      bar_sync(1, ncomp);  // every strip done: the queue is complete; everyone has read maxbits
+      if (tid == 0) ctl->maxbits[b] = 0u;
+      // Groups that failed the lead test (about 1e-4 of the pixels on Gaussian logits) are re-evaluated exactly -- operation by
+      // operation as torch does -- one pixel per warp at a time, spread over all warps.
+      const unsigned int nq = ctl->qcount[b];
+      if (nq > (unsigned)kFQueueCap) exact_all = true;  // overflow: redo the whole tile
+      if (!exact_all && nq) {
+        for (int j = tid >> 5; j < 4 * (int)nq; j += g.cwarps) {
+          const uint32_t e = queue[j >> 2];
+          exact_warp((int)(e >> 16), (int)(e & 0xffffu) + (j & 3));
+        }
+      }
+      if (!exact_all && nq) bar_sync(1, ncomp);  // label tile complete
+      if (exact_all) {  // non-finite / absurd magnitudes, empty presence vector: the whole tile follows the reference pixel by pixel
+        for (int j = tid; j < kST * kST; j += nt) {
+          const int yy = j / kST, xx = j - yy * kST;
+          float a[C];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const ViewDev& vw = p.view[v];
+            const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, false);
+            const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, false);
+            const int r0 = g.vbase[v] + Ly.i0 * 4 * vw.w, r1 = g.vbase[v] + Ly.i1 * 4 * vw.w;
+            const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+            const float* gsrc = vw.logits + (long long)n * vw.tile_stride;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              const int pl = c * 4 * vw.h * vw.w;
+              float x00, x01, x10, x11;
+              if (NB == 2) {
+                x00 = lds_f32(vb[v] + r0 + pl + c0); x01 = lds_f32(vb[v] + r0 + pl + c1);
+                x10 = lds_f32(vb[v] + r1 + pl + c0); x11 = lds_f32(vb[v] + r1 + pl + c1);
+              } else {
+                x00 = __ldg(gsrc + ((r0 + pl + c0) >> 2)); x01 = __ldg(gsrc + ((r0 + pl + c1) >> 2));
+                x10 = __ldg(gsrc + ((r1 + pl + c0) >> 2)); x11 = __ldg(gsrc + ((r1 + pl + c1) >> 2));
+              }
+              const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+              const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+              const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+              a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+            }
+          }
+          labsm[j] = (uint8_t)pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+        }
+        bar_sync(1, ncomp);
+      }
+    }
+
+    constexpr int UN = 4;
+    const long long vbase_px = (long long)n * tpx;
+    const bool vec_ok = ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
+    const int nvec = vec_ok ? (int)(tpx / 16) : 0;
+    uint4 bgn[UN], gn[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const int i = tid + u * nt;
+      gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      bgn[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < nvec) {
+        if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + vbase_px) + i);
+        if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + vbase_px) + i);
+      }
+    }
+
+    // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label)
+#ifdef PISTO_X_SKIP_VECTOR
+    if (false) {
+#else
+    {
+#endif
+      const long long base = vbase_px;
+      const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
+      const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
+      unsigned int cnt32[BINS];
+#pragma unroll
+      for (int i = 0; i < BINS; i++) cnt32[i] = 0;
+      for (int i0 = tid; i0 < nvec; i0 += UN * nt) {
+        uint4 bgv[UN], gv[UN], lv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          bgv[u] = bgn[u]; gv[u] = gn[u];
+          lv[u] = make_uint4(labc, labc, labc, labc);
+          if (i < nvec && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + (UN + u) * nt;
+          gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (i < nvec) {
+            if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+            if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+          }
+        }
+        if (do_conf) {
+#pragma unroll
+          for (int u = 0; u < UN; u += 2) {
+            const unsigned int gw[8] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w, gv[u + 1].x, gv[u + 1].y, gv[u + 1].z, gv[u + 1].w};
+            const unsigned int lw8[8] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w, lv[u + 1].x, lv[u + 1].y, lv[u + 1].z, lv[u + 1].w};
+            bitslice_count<C>(gw, lw8, cnt32);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          if (i < nvec && has_label) {
+            uint4 o = lv[u];
+            if (has_bg) {
+              const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+              const unsigned int bw[4] = {bgv[u].x, bgv[u].y, bgv[u].z, bgv[u].w};
+              unsigned int ow[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
+              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
+          }
+        }
+      }
+      if (do_conf) {
+#pragma unroll
+        for (int bn = 0; bn < BINS; bn++) {
+          const unsigned int cv = __reduce_add_sync(0xffffffffu, cnt32[bn]);
+          if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
+        }
+      }
+      for (int i = nvec * 16 + tid; i < (int)tpx; i += nt) {  // unaligned mask / label pointers
+        const unsigned int lab = multi ? labsm[i] : (unsigned)tp.single;
+        unsigned int o = lab;
+        if (has_bg && p.bg[base + i] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+        if (do_conf) {
+          const unsigned int gg = p.gt[base + i];
+          if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
+        }
+        if (has_label) p.label_out[base + i] = (uint8_t)o;
+      }
+    }
+    }  // !is_export
+#ifndef PISTO_X_SKIP_EXPORT
+    if (need_low) export_units(n, sb, vb);
+#endif
+    __syncwarp();
+    if (NB == 2 && (tid & 31) == 0) mbar_arrive(&ctl->empty[sb]);
+  }
+  if (do_conf) {
+    bar_sync(1, ncomp);
+    for (int i = tid; i < BINS; i += nt)
+      if (ctl->hist[i]) atomicAdd(&p.conf[i], (unsigned long long)ctl->hist[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int G, int VPG>
+static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, StaticGeom* g) {
+  constexpr int V = G * VPG;
+  memset(g, 0, sizeof(*g));
+  if (p.C != C || p.V != V || p.T_h != kST || p.T_w != kST) return false;
+  const bool low = p.lowres_out && p.low_fh > 0;
+  if (low && (p.low_h != kSLow || p.low_w != kSLow || nbuf != 2)) return false;
+  for (int v = 0; v < V; v++) {
+    const ViewDev& vw = p.view[v];
+    const int hh = st_h(G, v / VPG);
+    if (vw.h != hh || vw.w != hh || vw.map.ho != hh || vw.map.wo != hh) return false;
+    if (vw.map.ai != 1 || vw.map.aj != 0 || vw.map.bi != 0 || (vw.map.bj != 1 && vw.map.bj != -1) || vw.map.a0 != 0) return false;  // identity or hflip
+    g->vbase[v] = 4 * vw.map.b0;
+    g->vcol[v] = 4 * vw.map.bj;
+    // every constexpr table entry against the arithmetic every other kernel (and the oracle) uses
+    for (int y = 0; y < kST; y++) {
+      const Lerp L = pisto_src_index(vw.scale_h, y, hh, false);
+      const int s = y / kSR, r = y % kSR;
+      int i0 = s * (hh / 7) + st_i0rel(hh, r);
+      const float l1 = st_l1(hh, r);
+      const bool clamped = i0 < 0 || i0 >= hh - 1;
+      if (!clamped && (L.i0 != i0 || L.i1 != i0 + 1 || L.l1 != l1 || L.l0 != 1.f - l1)) return false;
+      if (clamped && L.i0 != (i0 < 0 ? 0 : hh - 1)) return false;
+      if (clamped && i0 < 0 && L.l1 != 0.f) return false;
+    }
+    for (int ly = 0; ly < kSLow; ly++) {
+      const Lerp L = pisto_src_index(vw.scale_h, 7 * ly + 3, hh, false);
+      if (L.i0 != lo_i0(hh, ly) || L.i1 != lo_i1(hh, ly) || L.l1 != lo_l1(hh, ly) || L.l0 != 1.f - lo_l1(hh, ly)) return false;
+    }
+    for (int x = 0; x < kST; x += 4) {  // the 4 columns of a thread lie within two adjacent source cells (3-tap loads)
+      const Lerp L0 = pisto_src_index(vw.scale_w, x, hh, false);
+      for (int c = 0; c < 4; c++) {
+        const Lerp L = pisto_src_index(vw.scale_w, x + c, hh, false);
+        if (L.i0 < L0.i0 || L.i0 > L0.i0 + 1) return false;
+        if (L.i1 != L.i0 && L.i1 != L.i0 + 1) return false;
+        if (L.i1 == L.i0 && L.i0 != hh - 1 && L.l1 != 0.f) return false;
+      }
+    }
+  }
+  for (int r = 0; r < kSR; r++)
+    for (int q = 0; q < G; q++) {
+      g->wtab[r][q] = st_l1(st_h(G, q), r) - 1.f;
+      if (st_adv(st_h(G, q), r)) g->adv[q] |= 1u << r;
+    }
+  g->aux = low ? kSAux : 0;
+  g->cwarps = kSCThreads / 32;
+  g->threads = kSCThreads + 32 * g->aux + 32;
+  int fl = 0;
+  for (int v = 0; v < V; v++) {
+    g->view_off[v] = fl;
+    fl += (C * p.view[v].h * p.view[v].w + 3 + 3 + 3) & ~3;
+  }
+  g->buf_floats = fl;
+  const float cE = 2.f * VPG + 4.f * G + 2.f * V + 20.f;
+  g->tau_coef = 2.f * cE * 5.9604645e-8f + 2.5e-7f;
+  g->tau_abs = p.dec.margin_abs * 1.01f;
+  constexpr int KPmax = C >= 4 ? 4 : C - 1;
+  int off = 0;
+  g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
+  g->col4_off = off; off += 16 * G * kSGX;
+  g->col4i_off = off; off += 4 * G * kSGX; off = (off + 15) & ~15;
+  g->lowtab_off = off; off += low ? 32 * (8 * V + 8 * G) : 0;
+  g->ymap_off = off; off += st_ybytes(G, G, KPmax);
+  g->queue_off = off; off += 4 * kFQueueCap;
+  g->lab_off = off; off += kST * kST;
+  off = (off + 127) & ~127;
+  g->views_off = off; off += nbuf * 4 * fl;
+  g->smem_bytes = off;
+  return off <= h->smem_optin - 1024;
+}
+
+template <int C, int G, int VPG, int F, int NB>
+int launch_static(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  StaticGeom g;
+  if (!make_static_geom<C, G, VPG>(h, p, NB, &g)) return PISTO_OK;
+  auto kern = fuse_static_kernel<C, G, VPG, F, NB>;
+  PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
+  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  const int grid = p.N < h->sm_count ? p.N : h->sm_count;
+  kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
+  *launched = true;
+  return PISTO_OK;
+}
+
+}  // namespace

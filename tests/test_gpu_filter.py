@@ -8,11 +8,11 @@ import torch
 from oracle import confusion as oconf
 from oracle import fuse as ofuse
 from pistoseg_b200 import ops, synthetic
-from pistoseg_b200._lib import (DECIDE_RAW, DECIDE_SOFTMAX, IMPL_FILTER2, IMPL_FILTER4, IMPL_GENERIC, IMPL_STREAM, MASK_FILL,
+from pistoseg_b200._lib import (DECIDE_RAW, DECIDE_SOFTMAX, IMPL_FILTER2, IMPL_FILTER4, IMPL_GENERIC, IMPL_STATIC, IMPL_STREAM, MASK_FILL,
                                 MASK_NEG_INF, MASK_NONE)
 
 pytestmark = pytest.mark.gpu
-FILTERS = [IMPL_FILTER2, IMPL_FILTER4]
+FILTERS = [IMPL_FILTER2, IMPL_FILTER4, IMPL_STATIC]  # generic filter kernel (2 / 4 columns per thread), shape-specialised kernel
 
 
 def run(cfg, cuda, impl, **kw):

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tests + bench (no ncu)
+# quick A/B: filter tests + bench_fuse of the default build and any extra libs given as arguments
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python -m pytest tests/test_gpu_filter.py tests/test_gpu_fuse.py -x -q -m gpu > gpurun_out/pytest_filter.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_filter.log
+bash tools/ab.sh "${IMPLS:-0}" "$@"
