@@ -83,8 +83,8 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
     rc = pisto_launch_fuse_fullres(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
   }
-  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6)) {
-    rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : (a->impl == 6 ? 3 : a->impl - 2), &launched);
+  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6 || a->impl == 7)) {
+    rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : (a->impl >= 6 ? a->impl - 3 : a->impl - 2), &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched && a->impl != 0) {
       pisto_set_error("pisto_fuse_argmax_confusion: impl=%d (filtered streaming kernel) has no instantiation for C=%d V=%d T=%dx%d with these options",

@@ -8,9 +8,10 @@ int pisto_launch_filter_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, i
 int pisto_launch_filter_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched);
 int pisto_launch_static_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh
 int pisto_launch_static_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
+int pisto_launch_duo_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);     // fuse_static.cuh, two CTAs per SM
 
 // np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch: the shape-specialised kernel of fuse_static.cuh
-// first), 3 = the shape-specialised kernel only
+// first), 3 = the shape-specialised kernel only, 4 = its two-CTAs-per-SM variant only
 int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   *launched = false;
   if (p.fuse_mode != PISTO_FUSE_LOGIT_MEAN) return PISTO_OK;       // softmax per view is not linear
@@ -22,6 +23,13 @@ int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st,
   if (bytes & 1) return PISTO_OK;
   bool views_aligned = true;
   for (int v = 0; v < p.V; v++) views_aligned &= ((uintptr_t)p.view[v].logits & 15) == 0;  // TMA source spans need a 16-byte aligned allocation start
+  if ((np == 0 || np == 4) && views_aligned && p.C == 3) {
+    static const bool no_duo = getenv("PISTO_NO_DUO") != nullptr;  // A/B knob
+    int rc = PISTO_OK;
+    if (np == 4 || !no_duo) rc = pisto_launch_duo_c3(h, p, st, launched);
+    if (rc != PISTO_OK || *launched || np == 4) return rc;
+  }
+  if (np == 4) return PISTO_OK;
   if ((np == 0 || np == 3) && views_aligned) {
     static const bool no_static = getenv("PISTO_NO_STATIC") != nullptr;  // A/B knob
     int rc = PISTO_OK;

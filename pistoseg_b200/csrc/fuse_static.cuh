@@ -72,6 +72,7 @@ __host__ __device__ constexpr int st_ybytes(int G, int g, int KP) {
 template <int OFF> __device__ __forceinline__ float lds_f32_o(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
 template <int OFF> __device__ __forceinline__ float2 lds_f2_o(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF)); return v; }
 template <int OFF> __device__ __forceinline__ float4 lds_f4_o(uint32_t a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_u8_o(uint32_t a, unsigned int v) { asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory"); }
 template <int OFF> __device__ __forceinline__ void sts_u32_o(uint32_t a, unsigned int v) { asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(OFF) : "memory"); }
 
 #ifndef PISTO_SU1
@@ -149,8 +150,9 @@ __device__ __forceinline__ void static_load_h(uint32_t a, const float4 L1, unsig
 // packed fma takes a uniform-register operand).
 // col4_t: address of the thread's float4 {l1 of its 4 columns} (group stride 16 * 56); col4i_t: address of its
 // (bytes-per-float * j0 | sel << 16) word (group stride 4 * 56); lab_a: label-tile address of (first row of the strip, x)
-template <int G, int K, int U>
-// Returns the rows of the strip (bit r) on which the thread's 4-pixel group failed the lead test.
+// Returns the rows of the strip (bit r) on which the thread's 4-pixel group failed the lead test.  PACK: the label tile holds 2 bits
+// per pixel (one byte per thread and row, row stride 56) instead of bytes.
+template <int G, int K, int U, bool PACK = false>
 __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_t col4_t, uint32_t col4i_t, uint32_t ymap_s, uint32_t lab_a, int strip,
                                                     const unsigned int (&c4)[4], float tau) {
   constexpr int KP = K == 3 ? 4 : K;
@@ -240,9 +242,10 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
         }
       unsigned int lab4;
       if (!labels_from_diffs<K, 2>(acc, c4, tau, lab4)) unc_blk |= 1u << rr;
-      sts_u32_o<rr * kST>(lab_a, lab4);
+      if constexpr (PACK) sts_u8_o<rr * kSGX>(lab_a, (lab4 * 0x01100440u) >> 24);  // 2 bits per pixel, fields in the order (0, 2, 1, 3)
+      else sts_u32_o<rr * kST>(lab_a, lab4);
     });
-    lab_a += U * kST;
+    lab_a += U * (PACK ? kSGX : kST);
     unc_rows |= unc_blk << (blk * U);
   }
   return unc_rows;
@@ -752,6 +755,449 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
   }
 }
 
+// =================================================================================================================================
+// Two tiles in flight per SM: the same algorithm in a 256-thread CTA that fits twice on an SM.  What makes it fit:
+//   * labels are staged at 2 bits per pixel (one byte per thread and row: 12.25 KB instead of 49 KB) and widened to bytes by the
+//     vector pass (PRMT with the 2-bit fields as selector nibbles over the constant 0x03020100);
+//   * ONE staging buffer: the 32x32 export -- the last reader of the raw views besides the rare exact pass -- runs right after the
+//     pre-pass, the buffer is released and the next tile's TMA lands while this tile's row loop and vector pass run (the exact
+//     pass reads its few samples from global memory, i.e. L2);
+//   * no producer warp: all 8 warps compute; warp 7 (which owns no strip of the row loop) re-arms the TMA.
+// The row loop's 7 strips run in two rounds over 4 x 56 threads.  While one CTA waits at a barrier or for its TMA, the other one
+// has the SM's issue slots.
+// =================================================================================================================================
+constexpr int kDThreads = 256;
+constexpr int kDSlots = 4;        // strips processed concurrently (56 threads each)
+constexpr int kDQueueCap = 256;
+
+// 16 labels (2 bits each: 4 bytes of the packed tile, byte = one thread-row = 4 pixels in field order (0, 2, 1, 3)) -> 16 bytes
+__device__ __forceinline__ uint4 duo_expand16(unsigned int w) {
+  unsigned int u, v, o[4];
+  asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(u) : "r"(w), "r"(0u));  // (b0, 0, b1, 0)
+  asm("prmt.b32 %0, %1, %2, 0x4342;" : "=r"(v) : "r"(w), "r"(0u));  // (b2, 0, b3, 0)
+  u = (u | (u << 6)) & 0x33333333u;  // per 16-bit half: nibbles = (p0, p1, p2, p3)
+  v = (v | (v << 6)) & 0x33333333u;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o[0]) : "r"(0x03020100u), "r"(0u), "r"(u));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o[1]) : "r"(0x03020100u), "r"(0u), "r"(u >> 16));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o[2]) : "r"(0x03020100u), "r"(0u), "r"(v));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(o[3]) : "r"(0x03020100u), "r"(0u), "r"(v >> 16));
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int C, int G, int VPG, int F>
+__global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ StaticGeom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int V = G * VPG;
+  constexpr bool RT = F < 0;
+  FCtl* ctl = reinterpret_cast<FCtl*>(smem_raw + g.ctl_off);
+  float4* col4 = reinterpret_cast<float4*>(smem_raw + g.col4_off);
+  uint32_t* col4i = reinterpret_cast<uint32_t*>(smem_raw + g.col4i_off);
+  uint2* lowtap = reinterpret_cast<uint2*>(smem_raw + g.lowtab_off);
+  float2* lowwt = reinterpret_cast<float2*>(smem_raw + g.lowtab_off + 32 * 8 * V);
+  float* ymap = reinterpret_cast<float*>(smem_raw + g.ymap_off);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(smem_raw + g.queue_off);
+  uint8_t* lab2 = smem_raw + g.lab_off;                                   // [224][56] packed labels
+  float* vsm = reinterpret_cast<float*>(smem_raw + g.views_off);
+
+  const int tid = threadIdx.x;
+  constexpr int nt = kDThreads;
+  const bool has_bg = RT ? (p.bg != nullptr) : ((F & 1) != 0);
+  const bool do_conf = RT ? (p.conf != nullptr && p.gt != nullptr) : ((F & 2) != 0);
+  const bool need_low = RT ? (p.lowres_out != nullptr && p.low_fh > 0) : ((F & 8) != 0);
+  const bool has_label = RT ? (p.label_out != nullptr) : ((F & 16) != 0);
+  constexpr int BINS = C * C;
+  constexpr int UNITS = C * kSNE;
+  constexpr int PROD = kDThreads - 32;  // first lane of warp 7: claims tiles and re-arms the TMA
+
+  if (tid == 0) {
+    mbar_init(&ctl->full[0], 1);
+    mbar_init(&ctl->empty[0], kDThreads / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ctl->maxbits[0] = ctl->maxbits[1] = 0u;
+    ctl->qcount[0] = ctl->qcount[1] = 0u;
+    ctl->lownext[0] = 0u;
+  }
+  for (int i = tid; i < 64; i += nt) ctl->hist[i] = 0;
+  for (int i = tid; i < G * kSGX; i += nt) {
+    const int gi = i / kSGX, gx = i - gi * kSGX;
+    const int h = gi == 0 ? st_h(G, 0) : (gi == 1 ? st_h(G, G > 1 ? 1 : 0) : st_h(G, G > 2 ? 2 : 0));
+    const float sc = (float)h / (float)kST;
+    Lerp L[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) L[c] = pisto_src_index(sc, 4 * gx + c, h, false);
+    col4[i] = make_float4(L[0].l1, L[1].l1, L[2].l1, L[3].l1);
+    unsigned int sel = 0;
+#pragma unroll
+    for (int c = 1; c < 4; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;
+    col4i[i] = (unsigned)(4 * L[0].i0) | (sel << 16);
+  }
+  if (need_low && tid < 32) {
+    static_for<0, V>([&](auto VI) {
+      constexpr int v = decltype(VI)::value, gi = v / VPG, h = st_h(G, gi);
+      const Lerp L = pisto_src_index((float)h / (float)kST, 7 * tid + 3, h, false);
+      lowtap[tid * V + v] = make_uint2((uint32_t)(g.vbase[v] + L.i0 * g.vcol[v]), (uint32_t)(g.vbase[v] + L.i1 * g.vcol[v]));
+      lowwt[tid * G + gi] = make_float2(L.l0, L.l1);
+    });
+  }
+
+  // fetch every view of tile n into the staging buffer (producer lane)
+  auto issue_tile = [&](int n) {
+    uint32_t total = 0;
+#pragma unroll 1
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      const char* start = reinterpret_cast<const char*>(vw.logits + (long long)n * vw.tile_stride);
+      const char* end = start + (size_t)C * vw.h * vw.w * sizeof(float);
+      const char* a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(start) & ~(uintptr_t)15);
+      const char* a1 = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(end) + 15) & ~(uintptr_t)15);
+      char* dst = reinterpret_cast<char*>(vsm + g.view_off[v]);
+      if (n == p.N - 1) {  // never read past the end of the caller's buffer: whole 16-byte units only, the tail by hand
+        a1 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(end) & ~(uintptr_t)15);
+        if (a1 < a0) a1 = a0;
+        const char* t = a1 > start ? a1 : start;
+        for (; t < end; t += 4) *reinterpret_cast<float*>(dst + (t - a0)) = *reinterpret_cast<const float*>(t);
+      }
+      const uint32_t bytes = (uint32_t)(a1 - a0);
+      if (bytes) bulk_g2s(dst, a0, bytes, &ctl->full[0]);
+      total += bytes;
+    }
+    mbar_arrive_expect_tx(&ctl->full[0], total);
+  };
+  // producer lane: publish tile `next` (claimed earlier) and start its transfers
+  auto publish = [&](int next, const TilePresence& ntp) {
+    const int tile = next < p.N ? next : -1;
+    ctl->tile[0] = tile;
+    ctl->pres_bits[0] = ntp.bits;
+    ctl->pres_single[0] = ntp.single;
+    ctl->lownext[0] = 0u;
+    if (tile >= 0 && (need_low || ntp.single < 0)) issue_tile(tile);
+    else mbar_arrive(&ctl->full[0]);
+    if (tile >= 0) {
+      const long long tile_px = (long long)kST * kST;
+      if (has_bg && ((uintptr_t)p.bg & 15) == 0) bulk_prefetch_l2(p.bg + tile * tile_px, (uint32_t)tile_px);
+      if (do_conf && ((uintptr_t)p.gt & 15) == 0) bulk_prefetch_l2(p.gt + tile * tile_px, (uint32_t)tile_px);
+    }
+  };
+
+  __syncthreads();
+
+  int next = 0;
+  TilePresence next_tp; next_tp.bits = 0u; next_tp.single = -1;
+  if (tid == PROD) {
+    next = atomicAdd(g.counter, 1);
+    if (next < p.N) next_tp = pisto_tile_presence(p, next);
+    publish(next, next_tp);
+  }
+
+  auto export_units = [&](int n, const uint32_t (&vb)[V]) {
+    const int lane = tid & 31;
+    uint32_t sA[V], sB[V];
+    float lx0[G], lx1[G];
+#pragma unroll
+    for (int v = 0; v < V; v++) { const uint2 t = lowtap[lane * V + v]; sA[v] = vb[v] + t.x; sB[v] = vb[v] + t.y; }
+#pragma unroll
+    for (int q = 0; q < G; q++) { const float2 t = lowwt[lane * G + q]; lx0[q] = t.x; lx1[q] = t.y; }
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = (int)atomicAdd(&ctl->lownext[0], 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= UNITS) break;
+      const int c = u / kSNE, e = u - c * kSNE;
+      static_for<0, kSNE>([&](auto EI) {
+        constexpr int E = decltype(EI)::value;
+        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(p, n, c, sA, sB, lx0, lx1);
+      });
+    }
+  };
+
+  const int grp = tid % kSGX, slot = tid / kSGX;
+  const bool worker = slot < kDSlots;
+  const int x = 4 * grp;
+  const uint32_t ymap_s = smem_u32(ymap);
+  const uint32_t col4_t = smem_u32(col4) + 16u * grp, col4i_t = smem_u32(col4i) + 4u * grp;
+  const uint32_t lab_s = smem_u32(lab2);
+  constexpr long long tpx = (long long)kST * kST;
+
+  for (int k = 0;; k++) {
+    const int b = k & 1;  // slot of the per-tile scratch (max, queue count)
+    mbar_wait(&ctl->full[0], k & 1);
+    const int n = ctl->tile[0];
+    if (n < 0) break;
+    TilePresence tp = pisto_tile_presence(p, n);
+    if (p.present) { tp.bits = ctl->pres_bits[0]; tp.single = ctl->pres_single[0]; }
+    const bool multi = tp.single < 0;
+    uint32_t vb[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const ViewDev& vw = p.view[v];
+      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+      vb[v] = smem_u32(vsm + g.view_off[v]) + sh;
+    }
+    int cls[C], P = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) cls[c] = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if ((tp.bits >> c) & 1u) {
+#pragma unroll
+        for (int q = 0; q < C; q++)
+          if (q == P) cls[q] = c;
+        P++;
+      }
+
+    if (multi && P >= 2) {
+      float mxf;
+      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tid, nt);
+      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tid, nt);
+      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
+      if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
+    }
+    // the 32x32 logits now (fills the wait for the slowest pre-pass warp); the staged views are read once more by the exact pass
+    if (need_low) export_units(n, vb);
+    // the staging buffer is released (and the next tile's TMA started) as soon as its last reader is done: here for single-label
+    // tiles, after the exact pass otherwise.  The next tile id and its presence vector are claimed by warp 7 -- which owns no
+    // strip of the row loop -- while the other warps are in the row loop.
+    auto release = [&]() {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&ctl->empty[0]);
+      if (tid == PROD) {
+        mbar_wait(&ctl->empty[0], k & 1);  // every warp is done with the staging buffer (and with the tile id / presence words)
+        publish(next, next_tp);
+      }
+    };
+    if (!multi) {
+      if (tid == PROD) {
+        next = atomicAdd(g.counter, 1);
+        next_tp.bits = 0u; next_tp.single = -1;
+        if (next < p.N) next_tp = pisto_tile_presence(p, next);
+      }
+      release();
+    }
+    __syncthreads();  // difference maps + max visible; every thread has left the previous tile's vector pass
+    if (tid == 0) ctl->qcount[b ^ 1] = 0u;
+    if (multi && tid == PROD) {
+      next = atomicAdd(g.counter, 1);
+      next_tp.bits = 0u; next_tp.single = -1;
+      if (next < p.N) next_tp = pisto_tile_presence(p, next);
+    }
+
+    // The byte masks of the vector pass' first batch are requested early (after the row loop / right away for single-label tiles),
+    // so that their latency is covered by the exact pass and the barriers; later batches are requested one step ahead.
+    constexpr int UN = 4;
+    const long long base = (long long)n * tpx;
+    const bool vec_ok = ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
+    const int nvec = vec_ok ? (int)(tpx / 16) : 0;
+    uint4 bgn[UN], gn[UN];
+    auto request_masks = [&]() {
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        const int i = tid + u * nt;
+        gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        bgn[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nvec) {
+          if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+          if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+        }
+      }
+    };
+
+    bool exact_all = false;
+    if (multi) {
+      float tau = 0.f;
+      if (P >= 2) {
+        const float A = __fmul_rn((float)V, __uint_as_float(ctl->maxbits[b]));
+        tau = __fmaf_rn(A, g.tau_coef, g.tau_abs);
+        if (!(A < 5e8f)) exact_all = true;
+      } else {
+        exact_all = true;
+      }
+      // exact sums of one pixel by a whole warp (lane = (view, class))
+      auto exact_warp = [&](int yy, int xx) -> int {
+        const int lane = tid & 31;
+        float o = 0.f;
+        if (lane < V * C) {
+          const int v = lane / C, c = lane - v * C;
+          const ViewDev& vw = p.view[v];
+          const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, false);
+          const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, false);
+          const int pl = g.vbase[v] + c * 4 * vw.h * vw.w;
+          const int r0 = pl + Ly.i0 * 4 * vw.w, r1 = pl + Ly.i1 * 4 * vw.w;
+          const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+          const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
+          const uint32_t base = smem_u32(vsm + g.view_off[v]) + sh;
+          const float x00 = lds_f32(base + r0 + c0), x01 = lds_f32(base + r0 + c1), x10 = lds_f32(base + r1 + c0), x11 = lds_f32(base + r1 + c1);
+          const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+          const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+          o = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+        }
+        float a[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          a[c] = __shfl_sync(0xffffffffu, o, c);
+#pragma unroll
+          for (int v = 1; v < V; v++) a[c] = __fadd_rn(a[c], __shfl_sync(0xffffffffu, o, (v * C + c) & 31));
+        }
+        return pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+      };
+      if (!exact_all) {
+        unsigned int c4[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) c4[q] = 0x01010101u * (unsigned)cls[q < C ? q : 0];
+#pragma unroll 1
+        for (int strip = slot; strip < kSS && worker; strip += kDSlots) {
+          const uint32_t lab_a = lab_s + (uint32_t)(strip * kSR * kSGX + grp);
+          unsigned int unc = 0;
+          if (P == 2) unc = static_rows<G, 1, kSU1, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (P == 3) unc = static_rows<G, 2, kSU2, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          while (unc) {
+            const int r = __ffs(unc) - 1;
+            unc &= unc - 1;
+            const unsigned int idx = atomicAdd(&ctl->qcount[b], 1u);
+            if (idx < (unsigned)kDQueueCap) queue[idx] = ((unsigned)(strip * kSR + r) << 16) | (unsigned)x;
+          }
+        }
+      }
+      __syncthreads();  // every strip done: the queue is complete; everyone has read maxbits
+      if (tid == 0) ctl->maxbits[b] = 0u;
+      request_masks();
+      const unsigned int nq = ctl->qcount[b];
+      if (nq > (unsigned)kDQueueCap) exact_all = true;  // overflow: redo the whole tile
+      if (!exact_all && nq) {
+        // queued groups, one pixel per warp at a time; the 2-bit field is patched with two word atomics (other fields of the word
+        // may be patched by other warps at the same time)
+        for (int j = tid >> 5; j < 4 * (int)nq; j += kDThreads / 32) {
+          const uint32_t e = queue[j >> 2];
+          const int yy = (int)(e >> 16), xx = (int)(e & 0xffffu) + (j & 3);
+          const int lab = exact_warp(yy, xx);
+          if ((tid & 31) == 0) {
+            const int bi = yy * kSGX + (xx >> 2);                          // byte of the packed tile
+            const int sh = 8 * (bi & 3) + 2 * ((0x3120 >> (4 * (xx & 3))) & 3);  // field order (0, 2, 1, 3)
+            unsigned int* w = reinterpret_cast<unsigned int*>(lab2) + (bi >> 2);
+            atomicAnd(w, ~(3u << sh));
+            atomicOr(w, (unsigned)lab << sh);
+          }
+        }
+        release();
+        __syncthreads();  // label tile complete
+      }
+      if (exact_all) {  // whole tile, one pixel per warp at a time would be slow: one pixel per thread, four pixels (one byte) at a time
+        for (int j = tid; j < kST * kSGX; j += nt) {
+          const int yy = j / kSGX, xg = j - yy * kSGX;
+          unsigned int byte = 0;
+#pragma unroll 1
+          for (int q = 0; q < 4; q++) {
+            const int xx = 4 * xg + q;
+            float a[C];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const ViewDev& vw = p.view[v];
+              const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, false);
+              const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, false);
+              const int r0 = g.vbase[v] + Ly.i0 * 4 * vw.w, r1 = g.vbase[v] + Ly.i1 * 4 * vw.w;
+              const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+#pragma unroll
+              for (int c = 0; c < C; c++) {
+                const int pl = c * 4 * vw.h * vw.w;
+                const float x00 = lds_f32(vb[v] + r0 + pl + c0), x01 = lds_f32(vb[v] + r0 + pl + c1);
+                const float x10 = lds_f32(vb[v] + r1 + pl + c0), x11 = lds_f32(vb[v] + r1 + pl + c1);
+                const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+                const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+                const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+                a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+              }
+            }
+            const int lab = pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
+            byte |= (unsigned)lab << (2 * ((0x3120 >> (4 * q)) & 3));
+          }
+          lab2[j] = (uint8_t)byte;
+        }
+        release();
+        __syncthreads();
+      }
+      if (!exact_all && !nq) release();
+    } else {
+      request_masks();
+    }
+
+    // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label)
+    {
+      const unsigned int labc = 0x01010101u * (unsigned)(multi ? 0 : tp.single), bgl4 = 0x01010101u * (unsigned)p.bg_label;
+      const unsigned int m4 = 0x01010101u * (unsigned)p.bg_match;
+      unsigned int cnt32[BINS];
+#pragma unroll
+      for (int i = 0; i < BINS; i++) cnt32[i] = 0;
+      for (int i0 = tid; i0 < nvec; i0 += UN * nt) {
+        uint4 bgv[UN], gv[UN], lv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          bgv[u] = bgn[u]; gv[u] = gn[u];  // requested one step ago
+          lv[u] = make_uint4(labc, labc, labc, labc);
+          if (i < nvec && multi) lv[u] = duo_expand16(lds_u32(lab_s + 4u * i));
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {  // request the next batch
+          const int i = i0 + (UN + u) * nt;
+          gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          if (i < nvec) {
+            if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+            if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+          }
+        }
+        if (do_conf) {
+#pragma unroll
+          for (int u = 0; u < UN; u += 2) {
+            const unsigned int gw[8] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w, gv[u + 1].x, gv[u + 1].y, gv[u + 1].z, gv[u + 1].w};
+            const unsigned int lw8[8] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w, lv[u + 1].x, lv[u + 1].y, lv[u + 1].z, lv[u + 1].w};
+            bitslice_count<C>(gw, lw8, cnt32);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; u++) {
+          const int i = i0 + u * nt;
+          if (i < nvec && has_label) {
+            uint4 o = lv[u];
+            if (has_bg) {
+              const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
+              const unsigned int bw[4] = {bgv[u].x, bgv[u].y, bgv[u].z, bgv[u].w};
+              unsigned int ow[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
+              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
+          }
+        }
+      }
+      if (do_conf && nvec) {
+#pragma unroll
+        for (int bn = 0; bn < BINS; bn++) {
+          const unsigned int cv = __reduce_add_sync(0xffffffffu, cnt32[bn]);
+          if ((tid & 31) == 0 && cv) atomicAdd(&ctl->hist[bn], cv);
+        }
+      }
+      for (int i = nvec * 16 + tid; i < (int)tpx; i += nt) {  // unaligned mask / label pointers
+        unsigned int lab = (unsigned)tp.single;
+        if (multi) lab = (lab2[i >> 2] >> (2 * ((0x3120 >> (4 * (i & 3))) & 3))) & 3u;
+        unsigned int o = lab;
+        if (has_bg && p.bg[base + i] == (uint8_t)p.bg_match) o = (unsigned)p.bg_label;
+        if (do_conf) {
+          const unsigned int gg = p.gt[base + i];
+          if (gg < (unsigned)C) atomicAdd(&ctl->hist[gg * C + lab], 1u);
+        }
+        if (has_label) p.label_out[base + i] = (uint8_t)o;
+      }
+    }
+  }
+  if (do_conf) {
+    __syncthreads();
+    for (int i = tid; i < BINS; i += nt)
+      if (ctl->hist[i]) atomicAdd(&p.conf[i], (unsigned long long)ctl->hist[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -824,6 +1270,45 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   g->views_off = off; off += nbuf * 4 * fl;
   g->smem_bytes = off;
   return off <= h->smem_optin - 1024;
+}
+
+// geometry of the two-CTAs-per-SM kernel: the checks and tables of make_static_geom, its own shared-memory layout
+template <int C, int G, int VPG>
+static bool make_duo_geom(const pisto_ctx* h, const FuseParams& p, StaticGeom* g) {
+  constexpr int V = G * VPG;
+  if (!make_static_geom<C, G, VPG>(h, p, 2, g)) return false;
+  const bool low = p.lowres_out && p.low_fh > 0;
+  g->aux = 0; g->cwarps = kDThreads / 32; g->threads = kDThreads;
+  constexpr int KPmax = C >= 4 ? 4 : C - 1;
+  int off = 0;
+  g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
+  g->col4_off = off; off += 16 * G * kSGX;
+  g->col4i_off = off; off += 4 * G * kSGX; off = (off + 15) & ~15;
+  g->lowtab_off = off; off += low ? 32 * (8 * V + 8 * G) : 0;
+  g->ymap_off = off; off += st_ybytes(G, G, KPmax);
+  g->queue_off = off; off += 4 * kDQueueCap;
+  g->lab_off = off; off += kST * kSGX;
+  off = (off + 127) & ~127;
+  g->views_off = off; off += 4 * g->buf_floats + 64;  // slack: nothing reads past the last view, but keep the export's immediate offsets in bounds
+  g->smem_bytes = off;
+  return 2 * (off + 1024) <= 233472;
+}
+
+template <int C, int G, int VPG, int F>
+int launch_duo(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  StaticGeom g;
+  if (!make_duo_geom<C, G, VPG>(h, p, &g)) return PISTO_OK;
+  auto kern = fuse_duo_kernel<C, G, VPG, F>;
+  PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
+  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  const int slots = 2 * h->sm_count;
+  const int grid = p.N < slots ? p.N : slots;
+  kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
+  *launched = true;
+  return PISTO_OK;
 }
 
 template <int C, int G, int VPG, int F, int NB>

@@ -8,14 +8,16 @@ import torch
 from oracle import confusion as oconf
 from oracle import fuse as ofuse
 from pistoseg_b200 import ops, synthetic
-from pistoseg_b200._lib import (DECIDE_RAW, DECIDE_SOFTMAX, IMPL_FILTER2, IMPL_FILTER4, IMPL_GENERIC, IMPL_STATIC, IMPL_STREAM, MASK_FILL,
+from pistoseg_b200._lib import (DECIDE_RAW, DECIDE_SOFTMAX, IMPL_FILTER2, IMPL_FILTER4, IMPL_DUO, IMPL_GENERIC, IMPL_STATIC, IMPL_STREAM, MASK_FILL,
                                 MASK_NEG_INF, MASK_NONE)
 
 pytestmark = pytest.mark.gpu
-FILTERS = [IMPL_FILTER2, IMPL_FILTER4, IMPL_STATIC]  # generic filter kernel (2 / 4 columns per thread), shape-specialised kernel
+FILTERS = [IMPL_FILTER2, IMPL_FILTER4, IMPL_STATIC, IMPL_DUO]  # generic filter kernel (2 / 4 columns per thread), shape-specialised kernels
 
 
 def run(cfg, cuda, impl, **kw):
+    if impl == IMPL_DUO and cfg["C"] != 3:
+        pytest.skip("two-CTAs-per-SM kernel: C = 3 only (C = 4 view sets do not fit twice in shared memory)")
     views = [v.to(cuda) for v in cfg["views"]]
     return ops.fuse_argmax_confusion(views, cfg["codes"], (cfg["T"], cfg["T"]), impl=impl,
                                      present=cfg.get("present"), bg=cfg.get("bg"), gt=cfg.get("gt"), **kw)

@@ -39,6 +39,10 @@ for name, cfg, kw in cases:
     row = {}
     for impl in impls:
         fn = lambda: ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), conf=conf, impl=impl, **args, **kw)
-        ms = timeit(fn)
+        try:
+            ms = timeit(fn)
+        except Exception as e:  # no instantiation of this kernel for the shape
+            row[impl] = None
+            continue
         row[impl] = round(N / ms * 1e3 / 1e6, 3)
     print(name, "Mtiles/s by impl:", json.dumps(row), flush=True)
