@@ -113,7 +113,7 @@ typedef struct {
   int32_t bg_match;    /* pixel is background iff bg[..] == bg_match (tissue==0: 0; gt==3: 3) */
   int32_t bg_label;    /* label written on background pixels (len(patch_label) / 3) */
   int32_t low_h, low_w;
-  int32_t impl;        /* 0 = auto, 1 = generic one-thread-per-pixel kernel, 2 = exact streaming kernel, 3 / 4 = filtered streaming kernel with 2 / 4 columns per thread, 5 = block-tiled filtered kernel (large tiles), 6 = shape-specialised filtered kernel (224x224 tiles, 21/28/35 px views), 7 = the same with two CTAs per SM */
+  int32_t impl;        /* 0 = auto, 1 = generic one-thread-per-pixel kernel, 2 = exact streaming kernel, 3 / 4 = filtered streaming kernel with 2 / 4 columns per thread, 5 = block-tiled filtered kernel (large tiles), 6 = shape-specialised filtered kernel (224x224 tiles, 21/28/35 px views), 7 = the same with two CTAs per SM, 8 = the same with 2 columns per thread (26 warps per SM) */
   const uint8_t* present; /* [N][C] 0/1 or NULL */
   const uint8_t* bg;      /* [N][T_h][T_w] or NULL */
   const uint8_t* gt;      /* [N][T_h][T_w] or NULL */

@@ -17,7 +17,7 @@ MAX_CLASSES = 8
 FUSE_LOGIT_MEAN, FUSE_PROB_MEAN = 0, 1
 MASK_NONE, MASK_FILL, MASK_NEG_INF, MASK_MULTIPLY = 0, 1, 2, 3
 DECIDE_SOFTMAX, DECIDE_RAW = 0, 1
-IMPL_AUTO, IMPL_GENERIC, IMPL_STREAM, IMPL_FILTER2, IMPL_FILTER4, IMPL_BAND, IMPL_STATIC, IMPL_DUO = 0, 1, 2, 3, 4, 5, 6, 7
+IMPL_AUTO, IMPL_GENERIC, IMPL_STREAM, IMPL_FILTER2, IMPL_FILTER4, IMPL_BAND, IMPL_STATIC, IMPL_DUO, IMPL_NARROW = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class PistoError(RuntimeError):

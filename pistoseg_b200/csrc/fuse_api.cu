@@ -83,7 +83,7 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
     rc = pisto_launch_fuse_fullres(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
   }
-  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6 || a->impl == 7)) {
+  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6 || a->impl == 7 || a->impl == 8)) {
     rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : (a->impl >= 6 ? a->impl - 3 : a->impl - 2), &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched && a->impl != 0) {

@@ -8,10 +8,11 @@ int pisto_launch_filter_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, i
 int pisto_launch_filter_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched);
 int pisto_launch_static_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh
 int pisto_launch_static_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
+int pisto_launch_narrow_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh, 2 columns per thread
 int pisto_launch_duo_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);     // fuse_static.cuh, two CTAs per SM
 
 // np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch: the shape-specialised kernel of fuse_static.cuh
-// first), 3 = the shape-specialised kernel only, 4 = its two-CTAs-per-SM variant only
+// first), 3 = the shape-specialised kernel only, 4 = its two-CTAs-per-SM variant only, 5 = its 2-columns-per-thread variant only
 int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, int np, bool* launched) {
   *launched = false;
   if (p.fuse_mode != PISTO_FUSE_LOGIT_MEAN) return PISTO_OK;       // softmax per view is not linear
@@ -26,15 +27,18 @@ int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st,
   if ((np == 0 || np == 4) && views_aligned && p.C == 3) {
     static const bool no_duo = getenv("PISTO_NO_DUO") != nullptr;  // A/B knob
     int rc = PISTO_OK;
-    if (np == 4 || !no_duo) rc = pisto_launch_duo_c3(h, p, st, launched);
+    // automatic dispatch: the single-view set (BASELINE config 1) only -- there two CTAs per SM measure +10 %; with three scale groups
+    // the one-CTA kernel below is faster (profiles/r02)
+    if (np == 4 || (!no_duo && p.V == 1)) rc = pisto_launch_duo_c3(h, p, st, launched);
     if (rc != PISTO_OK || *launched || np == 4) return rc;
   }
   if (np == 4) return PISTO_OK;
+  if (np == 5) return (views_aligned && p.C == 3) ? pisto_launch_narrow_c3(h, p, st, launched) : PISTO_OK;
   if ((np == 0 || np == 3) && views_aligned) {
     static const bool no_static = getenv("PISTO_NO_STATIC") != nullptr;  // A/B knob
     int rc = PISTO_OK;
     // automatic dispatch: where it is measured faster than the generic kernel (C = 3, three scales x flip); always when asked for
-    if (np == 3 || (!no_static && p.C == 3 && p.V == 6)) {
+    if (np == 3 || (!no_static && p.V == 6)) {
       if (p.C == 3) rc = pisto_launch_static_c3(h, p, st, launched);
       else if (p.C == 4) rc = pisto_launch_static_c4(h, p, st, launched);
     }

@@ -34,6 +34,7 @@ constexpr int kSS = 7;      // strips
 constexpr int kSR = 32;     // rows per strip
 constexpr int kSLow = 32;   // low-resolution side of the logit export
 constexpr int kSCThreads = 416;  // 13 compute warps (392 workers)
+constexpr int kSNarrowThreads = 832;  // 2 columns per thread: 25 compute warps (784 workers) + the producer warp
 
 // compile-time loop with the index as a constant expression
 template <int I, int N, class F>
@@ -103,17 +104,6 @@ struct StaticGeom {
   int ctl_off, col4_off, col4i_off, lowtab_off, ymap_off, queue_off, lab_off, views_off, smem_bytes;
   int* counter;
 };
-
-// rows of the strip whose 4-pixel group failed the lead test -> one queue entry per group: (y << 16) | x (x is a multiple of 4;
-// the exact pass re-evaluates the 4 pixels of an entry, spread over all warps)
-__device__ __noinline__ void static_push_groups(FCtl* ctl, uint32_t* queue, int b, int ys, int x, unsigned int rows) {
-  while (rows) {
-    const int r = __ffs(rows) - 1;
-    rows &= rows - 1;
-    const unsigned int idx = atomicAdd(&ctl->qcount[b], 1u);
-    if (idx < (unsigned)kFQueueCap) queue[idx] = ((unsigned)(ys + r) << 16) | (unsigned)x;
-  }
-}
 
 // horizontally interpolated values of the thread's 4 columns on one map row (3 adjacent source cells at `a`)
 template <int K, int OFF>
@@ -251,6 +241,186 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
   return unc_rows;
 }
 
+// ---- 2 columns per thread (NP = 1): half the registers per thread, twice the threads per row (112), so that an SM holds 26 warps
+// instead of 16 -- the row loop is bound by dependent-instruction latency, its throughput follows the number of resident warps.
+// col2_t: address of the thread's float2 {l1 of its 2 columns} (group stride 8 * 112); col2i_t: its (4 * j0 | sel << 16) word.
+template <int K, int OFF>
+__device__ __forceinline__ void static_load_h1(uint32_t a, const float2 L1, unsigned int sel, u64 (&H)[K]) {
+  const u64 l1a = pack2(L1.x, L1.y);
+  const u64 l0a = sub2(pack2(1.f, 1.f), l1a);
+  const bool s1 = (sel >> 1) & 1u;
+  float y0[K], y1[K], y2[K];
+  if constexpr (K == 1) {
+    y0[0] = lds_f32_o<OFF>(a); y1[0] = lds_f32_o<OFF + 4>(a); y2[0] = lds_f32_o<OFF + 8>(a);
+  } else if constexpr (K == 2) {
+    const float2 v0 = lds_f2_o<OFF>(a), v1 = lds_f2_o<OFF + 8>(a), v2 = lds_f2_o<OFF + 16>(a);
+    y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+  } else {
+    const float4 v0 = lds_f4_o<OFF>(a), v1 = lds_f4_o<OFF + 16>(a), v2 = lds_f4_o<OFF + 32>(a);
+    y0[0] = v0.x; y0[1 % K] = v0.y; y0[K - 1] = v0.z; y1[0] = v1.x; y1[1 % K] = v1.y; y1[K - 1] = v1.z;
+    y2[0] = v2.x; y2[1 % K] = v2.y; y2[K - 1] = v2.z;
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const float a1 = s1 ? y1[k] : y0[k], b1 = s1 ? y2[k] : y1[k];
+    H[k] = fma2(l0a, pack2(y0[k], a1), mul2(l1a, pack2(y1[k], b1)));
+  }
+}
+
+template <int G, int K, int U>
+__device__ __forceinline__ unsigned int static_rows1(const StaticGeom& g, uint32_t col2_t, uint32_t col2i_t, uint32_t ymap_s, uint32_t lab_a, int strip,
+                                                     const unsigned int (&c4)[4], float tau) {
+  constexpr int KP = K == 3 ? 4 : K;
+  constexpr int NBLK = kSR / U;
+  constexpr int GX1 = 2 * kSGX;
+  u64 Hb[G][K], Dh[G][K], base[K];
+  uint32_t yb[G];
+  unsigned int selm[G];
+  float2 L1[G];
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+    const uint32_t u = lds_u32(col2i_t + gi * 4u * GX1);
+    yb[gi] = ymap_s + st_ybytes(G, gi, KP) + KP * (u & 0xffffu) + (uint32_t)(strip * (h / 7) + st_i0rel(h, 0) + 1) * RS;
+    selm[gi] = u >> 16;
+    L1[gi] = lds_f2(col2_t + gi * 8u * GX1);
+    u64 Ha[K];
+    static_load_h1<K, 0>(yb[gi], L1[gi], selm[gi], Ha);
+    static_load_h1<K, RS>(yb[gi], L1[gi], selm[gi], Hb[gi]);
+#pragma unroll
+    for (int k = 0; k < K; k++) Dh[gi][k] = sub2(Hb[gi][k], Ha[k]);
+  });
+  auto rebase = [&]() {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      u64 s = Hb[0][k];
+#pragma unroll
+      for (int gi = 1; gi < G; gi++) s = add2(s, Hb[gi][k]);
+      base[k] = s;
+    }
+  };
+  rebase();
+  unsigned int unc_rows = 0;
+#pragma unroll 1
+  for (int blk = 0; blk < NBLK; blk++) {
+    unsigned int unc_blk = 0;
+    unsigned int advb[G];
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) advb[gi] = U == 32 ? 0u : g.adv[gi] >> (blk * U);
+    static_for<0, U>([&](auto RI) {
+      constexpr int rr = decltype(RI)::value;
+      bool moved = false;
+      static_for<0, G>([&](auto GI) {
+        constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+        constexpr bool some = st_adv_some(h, rr, U), all = st_adv_all(h, rr, U);
+        if constexpr (some) {
+          bool now = true;
+          if constexpr (!all) now = (advb[gi] >> rr) & 1u;
+          if (now) {
+            yb[gi] += RS;
+            u64 Hn[K];
+            static_load_h1<K, RS>(yb[gi], L1[gi], selm[gi], Hn);
+#pragma unroll
+            for (int k = 0; k < K; k++) { Dh[gi][k] = sub2(Hn[k], Hb[gi][k]); Hb[gi][k] = Hn[k]; }
+            moved = true;
+          }
+        }
+      });
+      if (moved) rebase();
+      float w[G];
+      if constexpr (U == 32) {
+        static_for<0, G>([&](auto GI) { constexpr int gi = decltype(GI)::value; w[gi] = st_l1(st_h(G, gi), rr) - 1.f; });
+      } else {
+        const float4 t = *reinterpret_cast<const float4*>(g.wtab[blk * U + rr]);
+        if (G > 2) w[G > 2 ? 2 : 0] = t.z;
+        if (G > 1) w[G > 1 ? 1 : 0] = t.y;
+        w[0] = t.x;
+      }
+      u64 acc[K][1];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        u64 a = base[k];
+#pragma unroll
+        for (int gi = 0; gi < G; gi++) a = fma2(pack2(w[gi], w[gi]), Dh[gi][k], a);
+        acc[k][0] = a;
+      }
+      unsigned int lab4;
+      if (!labels_from_diffs<K, 1>(acc, c4, tau, lab4)) unc_blk |= 1u << rr;
+      asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(lab_a), "h"((unsigned short)lab4), "n"(rr * kST) : "memory");
+    });
+    lab_a += U * kST;
+    unc_rows |= unc_blk << (blk * U);
+  }
+  return unc_rows;
+}
+
+// Rare path of the row loop: one output row whose 4-pixel (2-pixel) group failed the lead test is evaluated again from the difference
+// maps, pixel by pixel, and only the pixels whose own lead is within tau go to the exact pass (any evaluation of the interpolated
+// differences within the error bound of DESIGN.md 4.1 certifies the same order, so a pixel that passes here keeps the label the
+// row loop gave it).  Returns the uncertain pixels of the group as a bit mask.
+template <int G, int K>
+__device__ __noinline__ unsigned int static_recheck4(uint32_t col4_t, uint32_t col4i_t, uint32_t ymap_s, int y, float tau) {
+  constexpr int KP = K == 3 ? 4 : K;
+  u64 acc[K][2];
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+    const uint32_t u = lds_u32(col4i_t + gi * 4u * kSGX);
+    const uint32_t a0 = ymap_s + st_ybytes(G, gi, KP) + KP * (u & 0xffffu);
+    const float4 L1 = lds_f4(col4_t + gi * 16u * kSGX);
+    const Lerp Ly = pisto_src_index((float)h / (float)kST, y, h, false);
+    u64 Ha[K][2], Hb[K][2];
+    static_load_h<K, 0>(a0 + (uint32_t)(Ly.i0 + 1) * RS, L1, u >> 16, Ha);
+    static_load_h<K, 0>(a0 + (uint32_t)(Ly.i1 + 1) * RS, L1, u >> 16, Hb);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const u64 t = fma2(pack2(Ly.l0, Ly.l0), Ha[k][q], mul2(pack2(Ly.l1, Ly.l1), Hb[k][q]));
+        acc[k][q] = gi == 0 ? t : add2(acc[k][q], t);
+      }
+  });
+  const int cls[4] = {0, 1, 2, 3};
+  return uncertain_mask<K, 2, 4>(acc, cls, tau);
+}
+template <int G, int K>
+__device__ __noinline__ unsigned int static_recheck2(uint32_t col2_t, uint32_t col2i_t, uint32_t ymap_s, int y, float tau) {
+  constexpr int KP = K == 3 ? 4 : K;
+  constexpr int GX1 = 2 * kSGX;
+  u64 acc[K][1];
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
+    const uint32_t u = lds_u32(col2i_t + gi * 4u * GX1);
+    const uint32_t a0 = ymap_s + st_ybytes(G, gi, KP) + KP * (u & 0xffffu);
+    const float2 L1 = lds_f2(col2_t + gi * 8u * GX1);
+    const Lerp Ly = pisto_src_index((float)h / (float)kST, y, h, false);
+    u64 Ha[K], Hb[K];
+    static_load_h1<K, 0>(a0 + (uint32_t)(Ly.i0 + 1) * RS, L1, u >> 16, Ha);
+    static_load_h1<K, 0>(a0 + (uint32_t)(Ly.i1 + 1) * RS, L1, u >> 16, Hb);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const u64 t = fma2(pack2(Ly.l0, Ly.l0), Ha[k], mul2(pack2(Ly.l1, Ly.l1), Hb[k]));
+      acc[k][0] = gi == 0 ? t : add2(acc[k][0], t);
+    }
+  });
+  const int cls[4] = {0, 1, 2, 3};
+  return uncertain_mask<K, 1, 4>(acc, cls, tau);
+}
+// flagged rows of a strip -> per-pixel queue entries (y << 16) | x
+template <int G, int K, int NP>
+__device__ __forceinline__ void static_push_rows(FCtl* ctl, uint32_t* queue, int cap, int b, uint32_t colw_t, uint32_t coli_t, uint32_t ymap_s, int ys, int x,
+                                                 unsigned int rows, float tau) {
+  while (rows) {
+    const int y = ys + __ffs(rows) - 1;
+    rows &= rows - 1;
+    unsigned int m = NP == 2 ? static_recheck4<G, K>(colw_t, coli_t, ymap_s, y, tau) : static_recheck2<G, K>(colw_t, coli_t, ymap_s, y, tau);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned int idx = atomicAdd(&ctl->qcount[b], 1u);
+      if (idx < (unsigned)cap) queue[idx] = ((unsigned)y << 16) | (unsigned)(x + j);
+    }
+  }
+}
+
 // ---- pre-pass: Y[g][k] = sum over the views of group g of (x[c_{k+1}] - x[c_0]) in the de-augmented frame, maps padded by one
 // replicated row above / below and two replicated columns on the right; returns the thread's max |x| (NaN-propagating)
 template <int C, int G, int VPG, int K>
@@ -304,14 +474,14 @@ __device__ __forceinline__ float static_prepass(const StaticGeom& g, const uint3
 
 // a / V for the export (pisto_div_views with the IEEE division out of line: the unit code is replicated per row group)
 __device__ __noinline__ float static_div_slow(float a, float fV) { return __fdiv_rn(a, fV); }
-__device__ __forceinline__ float static_div_views(float a, const DecideCfg& cfg) {
+__device__ __forceinline__ float static_div_views(float a, float rcp_v, float fV) {
   // V = 1 and powers of two: rcp_v is exact, e = 0, r = q -- the same quotient pisto_div_views returns on its short cuts
-  const float q = __fmul_rn(a, cfg.rcp_v);
-  const float e = __fmaf_rn(-cfg.fV, q, a);
-  const float r = __fmaf_rn(e, cfg.rcp_v, q);
+  const float q = __fmul_rn(a, rcp_v);
+  const float e = __fmaf_rn(-fV, q, a);
+  const float r = __fmaf_rn(e, rcp_v, q);
   const float fa = fabsf(a);
   if (fa > 1e-30f && fa < 1e30f) return r;
-  return static_div_slow(a, cfg.fV);
+  return static_div_slow(a, fV);
 }
 
 // ---- 32x32 logit export: unit (class c, low-resolution rows RPU E .. RPU E + RPU - 1), lane = low-resolution column.  sA / sB:
@@ -319,8 +489,8 @@ __device__ __forceinline__ float static_div_views(float a, const DecideCfg& cfg)
 // flipped twin) share every constant, so they run through the same code (a two-trip loop); the sum starts from -0.f, the
 // identity of IEEE addition, so that the first view needs no special case.
 template <int C, int G, int VPG, int RPU, int E>
-__device__ __forceinline__ void static_export_unit(const FuseParams& p, int n, int c, const uint32_t (&sA)[G * VPG], const uint32_t (&sB)[G * VPG],
-                                                   const float (&lx0)[G], const float (&lx1)[G]) {
+__device__ __forceinline__ void static_export_unit(float* out_n, int c, const uint32_t (&sA)[G * VPG], const uint32_t (&sB)[G * VPG],
+                                                   const float (&lx0)[G], const float (&lx1)[G], float rcp_v, float fV) {
   float a[RPU];
 #pragma unroll
   for (int r = 0; r < RPU; r++) a[r] = -0.f;
@@ -344,13 +514,14 @@ __device__ __forceinline__ void static_export_unit(const FuseParams& p, int n, i
       });
     }
   });
-  float* outp = p.lowres_out + ((long long)(n * C + c) * kSLow + RPU * E) * kSLow + (threadIdx.x & 31);
+  float* outp = out_n + (c * kSLow + RPU * E) * kSLow + (threadIdx.x & 31);
 #pragma unroll
-  for (int r = 0; r < RPU; r++) outp[r * kSLow] = static_div_views(a[r], p.dec);
+  for (int r = 0; r < RPU; r++) outp[r * kSLow] = static_div_views(a[r], rcp_v, fV);
 }
 
-template <int C, int G, int VPG, int F, int NB>
-__global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ StaticGeom g) {
+template <int C, int G, int VPG, int F, int NB, int NP>
+__device__ __forceinline__ void fuse_static_body(const FuseParams& p, const StaticGeom& g) {
+  constexpr int GX = kST / (2 * NP);  // threads per output row
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int V = G * VPG;
   constexpr bool RT = F < 0;
@@ -383,17 +554,18 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
     ctl->qcount[0] = ctl->qcount[1] = 0u;
   }
   for (int i = tid; i < 64; i += nthreads) ctl->hist[i] = 0;
-  for (int i = tid; i < G * kSGX; i += nthreads) {
-    const int gi = i / kSGX, gx = i - gi * kSGX;
+  for (int i = tid; i < G * GX; i += nthreads) {
+    const int gi = i / GX, gx = i - gi * GX;
     const int h = gi == 0 ? st_h(G, 0) : (gi == 1 ? st_h(G, G > 1 ? 1 : 0) : st_h(G, G > 2 ? 2 : 0));
     const float sc = (float)h / (float)kST;
     Lerp L[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) L[c] = pisto_src_index(sc, 4 * gx + c, h, false);
-    col4[i] = make_float4(L[0].l1, L[1].l1, L[2].l1, L[3].l1);
+    for (int c = 0; c < 2 * NP; c++) L[c] = pisto_src_index(sc, 2 * NP * gx + c, h, false);
+    if (NP == 2) col4[i] = make_float4(L[0].l1, L[1].l1, L[2 * NP - 2].l1, L[2 * NP - 1].l1);
+    else reinterpret_cast<float2*>(col4)[i] = make_float2(L[0].l1, L[1].l1);
     unsigned int sel = 0;
 #pragma unroll
-    for (int c = 1; c < 4; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;  // 0 or 1 (checked on the host)
+    for (int c = 1; c < 2 * NP; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;  // 0 or 1 (checked on the host)
     col4i[i] = (unsigned)(4 * L[0].i0) | (sel << 16);
   }
 
@@ -471,6 +643,7 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
     for (int v = 0; v < V; v++) { const uint2 t = lowtap[lane * V + v]; sA[v] = vb[v] + t.x; sB[v] = vb[v] + t.y; }
 #pragma unroll
     for (int q = 0; q < G; q++) { const float2 t = lowwt[lane * G + q]; lx0[q] = t.x; lx1[q] = t.y; }
+    float* out_n = p.lowres_out + (long long)n * C * kSLow * kSLow;
     for (;;) {
       int u = 0;
       if (lane == 0) u = (int)atomicAdd(&ctl->lownext[b], 1u);
@@ -479,7 +652,7 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
       const int c = u / kSNE, e = u - c * kSNE;
       static_for<0, kSNE>([&](auto EI) {
         constexpr int E = decltype(EI)::value;
-        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(p, n, c, sA, sB, lx0, lx1);
+        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(out_n, c, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
       });
     }
   };
@@ -488,11 +661,11 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
   // the 32x32 units, the compute warps join them when their own work on the tile is done (the unit code exists once)
   const bool is_export = tid >= ncomp;
   if (is_export && !need_low) return;
-  const int grp = tid % kSGX, strip = min(tid / kSGX, kSS - 1);
-  const bool worker = tid < kSGX * kSS;
-  const int x = 4 * grp;
+  const int grp = tid % GX, strip = min(tid / GX, kSS - 1);
+  const bool worker = tid < GX * kSS;
+  const int x = 2 * NP * grp;
   const uint32_t ymap_s = smem_u32(ymap);
-  const uint32_t col4_t = smem_u32(col4) + 16u * grp, col4i_t = smem_u32(col4i) + 4u * grp;
+  const uint32_t col4_t = smem_u32(col4) + 8u * NP * grp, col4i_t = smem_u32(col4i) + 4u * grp;
   const uint32_t lab_s = smem_u32(labsm);
   const int nt = ncomp;
   constexpr long long tpx = (long long)kST * kST;
@@ -510,6 +683,9 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
       const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
       vb[v] = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
     }
+    // (Measured and dropped: mbarrier-based phase barriers at which a waiting warp works off export units.  The arrive / try_wait
+    // barrier itself cost 8 % against bar.sync and the filled waits returned less than that.)
+    auto phase_sync = [&](int) { bar_sync(1, ncomp); };
     if (!is_export) {
     TilePresence tp = pisto_tile_presence(p, n);
     if (p.present) { tp.bits = ctl->pres_bits[sb]; tp.single = ctl->pres_single[sb]; }
@@ -538,7 +714,7 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
       const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
-    bar_sync(1, ncomp);
+    phase_sync(0);  // difference maps + max visible; every thread has left the previous tile
     if (NB == 1 && (tid & 31) == 0) mbar_arrive(&ctl->empty[0]);
     if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone
 
@@ -599,24 +775,34 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 4; q++) c4[q] = 0x01010101u * (unsigned)cls[q < C ? q : 0];
         const uint32_t lab_a = lab_s + (uint32_t)(strip * kSR * kST + x);
-        if (P == 2) unc = static_rows<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
-        else if (P == 3) unc = static_rows<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
-        else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+        if constexpr (NP == 2) {
+          if (P == 2) unc = static_rows<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (P == 3) unc = static_rows<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+        } else {
+          if (P == 2) unc = static_rows1<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (P == 3) unc = static_rows1<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (C >= 4 && P == 4) unc = static_rows1<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+        }
       }
-      if (unc) static_push_groups(ctl, queue, b, strip * kSR, x, unc);
-      bar_sync(1, ncomp);  // every strip done: the queue is complete; everyone has read maxbits
+      if (unc) {
+        if (P == 2) static_push_rows<G, 1, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+        else if (P == 3) static_push_rows<G, 2, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+        else static_push_rows<G, (C >= 4 ? 3 : 1), NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+      }
+      phase_sync(1);  // every strip done: the queue is complete; everyone has read maxbits
       if (tid == 0) ctl->maxbits[b] = 0u;
-      // Groups that failed the lead test (about 1e-4 of the pixels on Gaussian logits) are re-evaluated exactly -- operation by
+      // Pixels that failed the lead test (about 1e-4 of them on Gaussian logits) are re-evaluated exactly -- operation by
       // operation as torch does -- one pixel per warp at a time, spread over all warps.
       const unsigned int nq = ctl->qcount[b];
       if (nq > (unsigned)kFQueueCap) exact_all = true;  // overflow: redo the whole tile
       if (!exact_all && nq) {
-        for (int j = tid >> 5; j < 4 * (int)nq; j += g.cwarps) {
-          const uint32_t e = queue[j >> 2];
-          exact_warp((int)(e >> 16), (int)(e & 0xffffu) + (j & 3));
+        for (int j = tid >> 5; j < (int)nq; j += g.cwarps) {
+          const uint32_t e = queue[j];
+          exact_warp((int)(e >> 16), (int)(e & 0xffffu));
         }
       }
-      if (!exact_all && nq) bar_sync(1, ncomp);  // label tile complete
+      if (!exact_all && nq) phase_sync(2);  // label tile complete
       if (exact_all) {  // non-finite / absurd magnitudes, empty presence vector: the whole tile follows the reference pixel by pixel
         for (int j = tid; j < kST * kST; j += nt) {
           const int yy = j / kST, xx = j - yy * kST;
@@ -648,7 +834,7 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
           }
           labsm[j] = (uint8_t)pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
         }
-        bar_sync(1, ncomp);
+        phase_sync(2);
       }
     }
 
@@ -753,6 +939,16 @@ __global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_consta
     for (int i = tid; i < BINS; i += nt)
       if (ctl->hist[i]) atomicAdd(&p.conf[i], (unsigned long long)ctl->hist[i]);
   }
+}
+
+// two entry points over the same body: 4 columns per thread (512 threads x 128 registers) and 2 columns per thread (832 x 72)
+template <int C, int G, int VPG, int F, int NB>
+__global__ void __launch_bounds__(512, 1) fuse_static_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ StaticGeom g) {
+  fuse_static_body<C, G, VPG, F, NB, 2>(p, g);
+}
+template <int C, int G, int VPG, int F, int NB>
+__global__ void __launch_bounds__(kSNarrowThreads, 1) fuse_narrow_kernel(const __grid_constant__ FuseParams p, const __grid_constant__ StaticGeom g) {
+  fuse_static_body<C, G, VPG, F, NB, 1>(p, g);
 }
 
 // =================================================================================================================================
@@ -897,6 +1093,7 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
     for (int v = 0; v < V; v++) { const uint2 t = lowtap[lane * V + v]; sA[v] = vb[v] + t.x; sB[v] = vb[v] + t.y; }
 #pragma unroll
     for (int q = 0; q < G; q++) { const float2 t = lowwt[lane * G + q]; lx0[q] = t.x; lx1[q] = t.y; }
+    float* out_n = p.lowres_out + (long long)n * C * kSLow * kSLow;
     for (;;) {
       int u = 0;
       if (lane == 0) u = (int)atomicAdd(&ctl->lownext[0], 1u);
@@ -905,7 +1102,7 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
       const int c = u / kSNE, e = u - c * kSNE;
       static_for<0, kSNE>([&](auto EI) {
         constexpr int E = decltype(EI)::value;
-        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(p, n, c, sA, sB, lx0, lx1);
+        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(out_n, c, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
       });
     }
   };
@@ -1051,11 +1248,10 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
           if (P == 2) unc = static_rows<G, 1, kSU1, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
           else if (P == 3) unc = static_rows<G, 2, kSU2, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
           else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2, true>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
-          while (unc) {
-            const int r = __ffs(unc) - 1;
-            unc &= unc - 1;
-            const unsigned int idx = atomicAdd(&ctl->qcount[b], 1u);
-            if (idx < (unsigned)kDQueueCap) queue[idx] = ((unsigned)(strip * kSR + r) << 16) | (unsigned)x;
+          if (unc) {
+            if (P == 2) static_push_rows<G, 1, 2>(ctl, queue, kDQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+            else if (P == 3) static_push_rows<G, 2, 2>(ctl, queue, kDQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+            else static_push_rows<G, (C >= 4 ? 3 : 1), 2>(ctl, queue, kDQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
           }
         }
       }
@@ -1067,9 +1263,9 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
       if (!exact_all && nq) {
         // queued groups, one pixel per warp at a time; the 2-bit field is patched with two word atomics (other fields of the word
         // may be patched by other warps at the same time)
-        for (int j = tid >> 5; j < 4 * (int)nq; j += kDThreads / 32) {
-          const uint32_t e = queue[j >> 2];
-          const int yy = (int)(e >> 16), xx = (int)(e & 0xffffu) + (j & 3);
+        for (int j = tid >> 5; j < (int)nq; j += kDThreads / 32) {
+          const uint32_t e = queue[j];
+          const int yy = (int)(e >> 16), xx = (int)(e & 0xffffu);
           const int lab = exact_warp(yy, xx);
           if ((tid & 31) == 0) {
             const int bi = yy * kSGX + (xx >> 2);                          // byte of the packed tile
@@ -1202,7 +1398,7 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, int G, int VPG>
-static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, StaticGeom* g) {
+static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, StaticGeom* g, int np = 2) {
   constexpr int V = G * VPG;
   memset(g, 0, sizeof(*g));
   if (p.C != C || p.V != V || p.T_h != kST || p.T_w != kST) return false;
@@ -1246,8 +1442,8 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
       if (st_adv(st_h(G, q), r)) g->adv[q] |= 1u << r;
     }
   g->aux = low ? kSAux : 0;
-  g->cwarps = kSCThreads / 32;
-  g->threads = kSCThreads + 32 * g->aux + 32;
+  g->cwarps = (kST / (2 * np) * kSS + 31) / 32;
+  g->threads = g->cwarps * 32 + 32 * g->aux + 32;
   int fl = 0;
   for (int v = 0; v < V; v++) {
     g->view_off[v] = fl;
@@ -1260,8 +1456,8 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   constexpr int KPmax = C >= 4 ? 4 : C - 1;
   int off = 0;
   g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
-  g->col4_off = off; off += 16 * G * kSGX;
-  g->col4i_off = off; off += 4 * G * kSGX; off = (off + 15) & ~15;
+  g->col4_off = off; off += 16 * G * kSGX;                        // [G][56] float4, or [G][112] float2
+  g->col4i_off = off; off += 4 * G * 2 * kSGX; off = (off + 15) & ~15;
   g->lowtab_off = off; off += low ? 32 * (8 * V + 8 * G) : 0;
   g->ymap_off = off; off += st_ybytes(G, G, KPmax);
   g->queue_off = off; off += 4 * kFQueueCap;
@@ -1304,6 +1500,22 @@ int launch_duo(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launche
   PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
   const int slots = 2 * h->sm_count;
   const int grid = p.N < slots ? p.N : slots;
+  kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
+  h->launches++;
+  PISTO_CUDA(cudaGetLastError());
+  *launched = true;
+  return PISTO_OK;
+}
+
+template <int C, int G, int VPG, int F, int NB>
+int launch_narrow(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  StaticGeom g;
+  if (!make_static_geom<C, G, VPG>(h, p, NB, &g, 1) || g.threads > kSNarrowThreads) return PISTO_OK;
+  auto kern = fuse_narrow_kernel<C, G, VPG, F, NB>;
+  PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
+  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());

@@ -15,6 +15,16 @@ int pisto_launch_duo_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool
   return PISTO_OK;
 }
 
+// 2 columns per thread, 26 warps per SM (fuse_narrow_kernel)
+int pisto_launch_narrow_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  const int f = pisto_filter_flags(p);
+  if (p.V == 6) {
+    if (f == 25) return launch_narrow<3, 3, 2, 25, 2>(h, p, st, launched);
+    if (f == 17) return launch_narrow<3, 3, 2, 17, 2>(h, p, st, launched);
+  }
+  return PISTO_OK;
+}
+
 int pisto_launch_static_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   const int f = pisto_filter_flags(p);
   if (p.V == 6) {
