@@ -53,7 +53,7 @@ extern "C" int pisto_destroy(pisto_handle_t h) {
   if (h->sched) { cudaSetDevice(h->device); cudaFree(h->sched); }
   if (h->pipe_ready) {
     cudaSetDevice(h->device);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < PISTO_PIPE_SLOTS; i++) {
       if (h->pipe_dev[i]) cudaFree(h->pipe_dev[i]);
       if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
       if (h->pipe_t1[i]) cudaEventDestroy(h->pipe_t1[i]);

@@ -16,6 +16,7 @@
 #define PISTO_MAX_VIEWS 16
 #define PISTO_MAX_CLASSES 8
 #define PISTO_SCHED_SLOTS 256
+#define PISTO_PIPE_SLOTS 3   // chunks in flight in the host-buffer pipeline (H2D of one, kernel of another, D2H of a third)
 
 struct pisto_ctx {
   int device;
@@ -25,11 +26,11 @@ struct pisto_ctx {
   int* sched;       // ring of device tile counters for the persistent kernels' dynamic scheduler
   unsigned int sched_next;
   // resources of the host-buffer (e2e) pipeline, created lazily
-  cudaStream_t pipe_stream[2];
-  cudaEvent_t pipe_done[2];
-  void* pipe_dev[2];
-  size_t pipe_dev_bytes[2];
-  cudaEvent_t pipe_t0, pipe_t1[2];  // timing of the last host-buffer call (device clock)
+  cudaStream_t pipe_stream[PISTO_PIPE_SLOTS];
+  cudaEvent_t pipe_done[PISTO_PIPE_SLOTS];
+  void* pipe_dev[PISTO_PIPE_SLOTS];
+  size_t pipe_dev_bytes[PISTO_PIPE_SLOTS];
+  cudaEvent_t pipe_t0, pipe_t1[PISTO_PIPE_SLOTS];  // timing of the last host-buffer call (device clock)
   float pipe_last_ms;
   bool pipe_ready;
 };

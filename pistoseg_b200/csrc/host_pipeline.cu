@@ -1,10 +1,13 @@
 // pisto_fuse_argmax_confusion_host: the same fused call with HOST buffers -- what a caller holding numpy / CPU-torch
 // data (the reference's DataLoader output) invokes, and what bench.py's end-to-end ("e2e") number times.
 //
-// Tiles are processed in chunks; chunk k uses device slot k%2 and stream k%2:  H2D of the chunk's view slices and
+// Tiles are processed in chunks; chunk k uses device slot k%3 and stream k%3:  H2D of the chunk's view slices and
 // byte masks -> fused kernel -> D2H of labels / 32x32 logits, so that the copy engines (both directions) and the
 // SMs work on different chunks at the same time.  Host buffers should be pinned (cudaHostAlloc / torch pin_memory)
 // for the copies to be asynchronous; pageable memory still works, serialised by the driver.
+// View logits may also be DEVICE pointers (the reference's own dataflow: the backbone output never leaves the GPU, only
+// `tissue` comes from the DataLoader and labels / 32x32 logits go back -- infer_pseudo_masks.py:119-137); such views are used in
+// place, only the byte masks are uploaded.
 #include "fuse_common.cuh"
 
 int pisto_build_fuse_params(const pisto_view_t* views, int V, const pisto_fuse_args_t* a, FuseParams* out, bool* low_via_resize);
@@ -15,7 +18,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ensure_pipe(pisto_ctx* h, size_t bytes) {
   if (!h->pipe_ready) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < PISTO_PIPE_SLOTS; i++) {
       PISTO_CUDA(cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking));
       PISTO_CUDA(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
       PISTO_CUDA(cudaEventCreate(&h->pipe_t1[i]));
@@ -23,7 +26,7 @@ int ensure_pipe(pisto_ctx* h, size_t bytes) {
     PISTO_CUDA(cudaEventCreate(&h->pipe_t0));
     h->pipe_ready = true;
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < PISTO_PIPE_SLOTS; i++) {
     if (h->pipe_dev_bytes[i] < bytes) {
       if (h->pipe_dev[i]) { PISTO_CUDA(cudaStreamSynchronize(h->pipe_stream[i])); PISTO_CUDA(cudaFree(h->pipe_dev[i])); h->pipe_dev[i] = nullptr; h->pipe_dev_bytes[i] = 0; }
       PISTO_CUDA(cudaMalloc(&h->pipe_dev[i], bytes));
@@ -49,12 +52,18 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
   // device slot layout (per chunk), every region 256-byte aligned
   size_t off = 0;
   size_t view_off[PISTO_MAX_VIEWS], view_tile_bytes[PISTO_MAX_VIEWS];
+  bool view_on_device[PISTO_MAX_VIEWS];
   for (int v = 0; v < V; v++) {
+    cudaPointerAttributes pa;
+    view_on_device[v] = views[v].logits && cudaPointerGetAttributes(&pa, views[v].logits) == cudaSuccess &&
+                        (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged);
+    cudaGetLastError();  // an unregistered (pageable) host pointer is not an error here
     PISTO_REQUIRE(views[v].logits && views[v].h >= 1 && views[v].w >= 1, "pisto_fuse_argmax_confusion_host: view %d invalid", v);
     PISTO_REQUIRE(views[v].tile_stride == 0 || views[v].tile_stride == (int64_t)C * views[v].h * views[v].w,
                   "pisto_fuse_argmax_confusion_host: strided host views are not supported");
     view_tile_bytes[v] = (size_t)C * views[v].h * views[v].w * sizeof(float);
-    view_off[v] = off; off = align_up(off + view_tile_bytes[v] * chunk, 256);
+    view_off[v] = off;
+    if (!view_on_device[v]) off = align_up(off + view_tile_bytes[v] * chunk, 256);
   }
   size_t o_present = off; if (a->present) off = align_up(off + (size_t)chunk * C, 256);
   size_t o_bg = off; if (a->bg) off = align_up(off + px * chunk, 256);
@@ -70,21 +79,25 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
 
   // device-clock timing of the whole call: t0 on stream 0 (stream 1 waits for it), one end event per stream
   PISTO_CUDA(cudaEventRecord(h->pipe_t0, h->pipe_stream[0]));
-  PISTO_CUDA(cudaStreamWaitEvent(h->pipe_stream[1], h->pipe_t0, 0));
-  if (a->conf) for (int s = 0; s < 2; s++) PISTO_CUDA(cudaMemsetAsync((char*)h->pipe_dev[s] + o_conf, 0, (size_t)C * C * sizeof(unsigned long long), h->pipe_stream[s]));
+  for (int s = 1; s < PISTO_PIPE_SLOTS; s++) PISTO_CUDA(cudaStreamWaitEvent(h->pipe_stream[s], h->pipe_t0, 0));
+  if (a->conf) for (int s = 0; s < PISTO_PIPE_SLOTS; s++) PISTO_CUDA(cudaMemsetAsync((char*)h->pipe_dev[s] + o_conf, 0, (size_t)C * C * sizeof(unsigned long long), h->pipe_stream[s]));
 
   int k = 0;
   for (int n0 = 0; n0 < a->N; n0 += chunk, k++) {
-    const int s = k & 1;
+    const int s = k % PISTO_PIPE_SLOTS;
     const int nn = a->N - n0 < chunk ? a->N - n0 : chunk;
     cudaStream_t st = h->pipe_stream[s];
     char* d = (char*)h->pipe_dev[s];
     pisto_view_t dv[PISTO_MAX_VIEWS];
     for (int v = 0; v < V; v++) {
       dv[v] = views[v];
-      dv[v].logits = (const float*)(d + view_off[v]);
       dv[v].tile_stride = 0;
-      PISTO_CUDA(cudaMemcpyAsync(d + view_off[v], (const char*)views[v].logits + view_tile_bytes[v] * n0, view_tile_bytes[v] * nn, cudaMemcpyHostToDevice, st));
+      if (view_on_device[v]) {  // already on the GPU (the backbone's output): used in place
+        dv[v].logits = (const float*)((const char*)views[v].logits + view_tile_bytes[v] * n0);
+      } else {
+        dv[v].logits = (const float*)(d + view_off[v]);
+        PISTO_CUDA(cudaMemcpyAsync(d + view_off[v], (const char*)views[v].logits + view_tile_bytes[v] * n0, view_tile_bytes[v] * nn, cudaMemcpyHostToDevice, st));
+      }
     }
     pisto_fuse_args_t da = *a;
     da.N = nn;
@@ -103,19 +116,22 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
     if (a->entropy_out) PISTO_CUDA(cudaMemcpyAsync(a->entropy_out + px * n0, d + o_ent, px * nn * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (a->lowres_out) PISTO_CUDA(cudaMemcpyAsync(a->lowres_out + low_px * n0 * C, d + o_low, low_px * nn * C * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  unsigned long long part[2][PISTO_MAX_CLASSES * PISTO_MAX_CLASSES];
-  for (int s = 0; s < 2; s++) {
+  unsigned long long part[PISTO_PIPE_SLOTS][PISTO_MAX_CLASSES * PISTO_MAX_CLASSES];
+  for (int s = 0; s < PISTO_PIPE_SLOTS; s++) {
     if (a->conf) PISTO_CUDA(cudaMemcpyAsync(part[s], (char*)h->pipe_dev[s] + o_conf, (size_t)C * C * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->pipe_stream[s]));
     PISTO_CUDA(cudaEventRecord(h->pipe_t1[s], h->pipe_stream[s]));
     PISTO_CUDA(cudaStreamSynchronize(h->pipe_stream[s]));
   }
   {
-    float m0 = 0.f, m1 = 0.f;
-    PISTO_CUDA(cudaEventElapsedTime(&m0, h->pipe_t0, h->pipe_t1[0]));
-    PISTO_CUDA(cudaEventElapsedTime(&m1, h->pipe_t0, h->pipe_t1[1]));
-    h->pipe_last_ms = m0 > m1 ? m0 : m1;
+    float mx = 0.f;
+    for (int s = 0; s < PISTO_PIPE_SLOTS; s++) {
+      float m = 0.f;
+      PISTO_CUDA(cudaEventElapsedTime(&m, h->pipe_t0, h->pipe_t1[s]));
+      mx = m > mx ? m : mx;
+    }
+    h->pipe_last_ms = mx;
   }
-  if (a->conf) for (int i = 0; i < C * C; i++) a->conf[i] += part[0][i] + part[1][i];
+  if (a->conf) for (int i = 0; i < C * C; i++) for (int s = 0; s < PISTO_PIPE_SLOTS; s++) a->conf[i] += part[s][i];
   return PISTO_OK;
 }
 

@@ -153,7 +153,9 @@ def fuse_argmax_confusion_host(views, xforms=None, size=None, *, fuse_mode=FUSE_
                                decide=DECIDE_SOFTMAX, present=None, bg=None, bg_match=0, bg_label=None, gt=None,
                                conf=None, want_labels=True, lowres=None, chunk=1024, device=0, out=None):
     """Same op with HOST buffers (CPU torch tensors, ideally pinned): H2D, kernel and D2H are pipelined inside the
-    library (pisto_fuse_argmax_confusion_host).  This is the call bench.py's "e2e" number times.
+    library (pisto_fuse_argmax_confusion_host).  This is the call bench.py's "e2e" number times.  The views may also be CUDA
+    tensors (the reference's own dataflow, infer_pseudo_masks.py:119-137: the backbone output stays on the GPU, only ``tissue``
+    comes from the host and labels / 32x32 logits go back): then only the byte masks are uploaded.
     ``out`` may carry preallocated pinned 'labels' / 'lowres' tensors.  conf is an int64 [C,C] CPU tensor (accumulated)."""
     v0 = views[0]
     N, C_ = int(v0.shape[0]), int(v0.shape[1])
@@ -163,8 +165,10 @@ def fuse_argmax_confusion_host(views, xforms=None, size=None, *, fuse_mode=FUSE_
     T_h, T_w = int(size[0]), int(size[1])
     arr = (_lib.View * len(views))()
     for i, (v, code) in enumerate(zip(views, xforms)):
-        if v.is_cuda or v.dtype != torch.float32 or not v.is_contiguous():
-            raise _lib.PistoError("host views must be contiguous float32 CPU tensors")
+        if v.dtype != torch.float32 or not v.is_contiguous():
+            raise _lib.PistoError("views must be contiguous float32 tensors (CPU, ideally pinned; or already on the GPU)")
+        if v.is_cuda and _dev_index(v) != int(device):
+            raise _lib.PistoError("device-resident views must live on the device the call runs on")
         arr[i].logits = v.data_ptr(); arr[i].tile_stride = 0
         arr[i].h, arr[i].w, arr[i].xform = int(v.shape[2]), int(v.shape[3]), int(code)
     out = dict(out or {})
