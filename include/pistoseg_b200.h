@@ -140,6 +140,26 @@ double pisto_last_pipeline_ms(pisto_handle_t h);
 int pisto_selftest_div(pisto_handle_t h, int V, unsigned long long* mismatches_dev, pisto_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------------- */
+/* revise-mask tail: PIL mode-'P' resize (= NEAREST, ImagingScaleAffine) to the original size, then   */
+/* mask[background > 0] = bg_value AT THE ORIGINAL RESOLUTION (infer_revise_masks.py:152-155,164-174). */
+/* in [n_tiles][sh][sw] u8 label maps (device); one descriptor per output image: which tile, its      */
+/* original (h, w), offsets of its row / column source-index tables in index_pool (int32, built by    */
+/* the caller exactly as PIL accumulates them), of its background mask in bg_pool (-1: none) and of    */
+/* its output in out_pool.  All pools and the descriptors are device memory.                           */
+/* -------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t tile;            /* index into in[] */
+  int32_t h, w;            /* original size */
+  int32_t reserved;
+  int64_t iy_off, ix_off;  /* int32 elements into index_pool: h row indices, w column indices */
+  int64_t bg_off;          /* bytes into bg_pool ([h][w] u8), or -1 */
+  int64_t out_off;         /* bytes into out_pool ([h][w] u8) */
+} pisto_resize_desc_t;
+
+int pisto_resize_nearest_bg(pisto_handle_t h, const uint8_t* in, int n_tiles, int sh, int sw, const pisto_resize_desc_t* desc, int n_desc,
+                            const int32_t* index_pool, const uint8_t* bg_pool, uint8_t* out_pool, int bg_value, pisto_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------- */
 /* bilinear resize, align_corners=False: replaces interpolate_tensor / F.interpolate(mode='bilinear') */
 /*   infer_pseudo_masks.py:89-90, segmentation_test.py:88-89,197, prepare_seg_inputs.py:116,131,137   */
 /*   dtype: 0 = float32, 1 = float64.  in [NC][hi][wi] -> out [NC][ho][wo]                            */

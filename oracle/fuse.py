@@ -100,3 +100,33 @@ def revise_masks(x, label, background=None, bg_value=3):
         m = m.copy()
         m[np.asarray(background) > 0] = bg_value
     return m
+
+
+def revise_masks_to_original(x, label, original_hw, background=None, bg_value=3):
+    """``infer_revise_masks.py:137-143,152-155`` for ONE head of ONE tile batch: ``(x * label)[:, 1:]`` -> ``argmax(dim=1)`` ->
+    PIL mode-P resize to the original ``(w, h)`` (``resample=Image.BILINEAR`` is asked for, but PIL resizes mode 'P' -- like '1' --
+    with NEAREST whatever the argument) -> ``mask[background > 0] = 3`` AT THE ORIGINAL RESOLUTION.
+    x [B,C+1,S,S] torch; original_hw: list of (h, w); background: list of [h,w] arrays or None.  Returns a list of uint8 [h,w]."""
+    from PIL import Image
+    m = revise_masks(x, label)
+    out = []
+    for j, (h, w) in enumerate(original_hw):
+        r = np.array(Image.fromarray(np.uint8(m[j]), mode='P').resize((int(w), int(h)), resample=Image.BILINEAR))
+        if background is not None:
+            r[np.asarray(background[j]) > 0] = bg_value
+        out.append(r)
+    return out
+
+
+def nearest_resize_index(n_in, n_out):
+    """Source index of PIL's NEAREST resize along one axis (Pillow ``ImagingScaleAffine``, the path ``Image.resize`` takes for
+    NEAREST without rotation): ``xo = 0.5 * a; for x: idx[x] = int(xo); xo += a`` with ``a = n_in / n_out`` in double -- the
+    ACCUMULATED double, not ``(x + 0.5) * a`` (they differ where the product is an integer).  Checked against ``Image.resize``
+    in tests/test_oracle_golden.py."""
+    a = n_in / n_out
+    xo = a * 0.5
+    out = np.empty(n_out, np.int64)
+    for x in range(n_out):
+        out[x] = int(xo)
+        xo += a
+    return np.minimum(out, n_in - 1)

@@ -43,6 +43,11 @@ class TilePos(C.Structure):
     _fields_ = [("y", C.c_int32), ("x", C.c_int32), ("crop_h", C.c_int32), ("crop_w", C.c_int32)]
 
 
+class ResizeDesc(C.Structure):
+    _fields_ = [("tile", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("reserved", C.c_int32),
+                ("iy_off", C.c_int64), ("ix_off", C.c_int64), ("bg_off", C.c_int64), ("out_off", C.c_int64)]
+
+
 class MosaicQuad(C.Structure):
     _fields_ = [("flip", C.c_int32), ("warp", C.c_int32), ("crop_y", C.c_int32), ("crop_x", C.c_int32),
                 ("minv", C.c_double * 6)]
@@ -73,6 +78,7 @@ SYMBOLS = {
     "pisto_stitch_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "pisto_canvas_normalize": (_i, [_vp, _vp, _vp, _i, _i64, _d, _vp]),
     "pisto_canvas_axpy": (_i, [_vp, _vp, _vp, _i64, _d, _vp]),
+    "pisto_resize_nearest_bg": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "pisto_argmax_f64": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "pisto_mosaic_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pisto_mosaic_pack_pool": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),

@@ -328,3 +328,20 @@ def get_background(rgb, thresh=200, min_size=50):
     scratch = torch.empty(2 * N * H * W, dtype=torch.int32, device=x.device)
     _lib.check(_lib.load().pisto_get_background(_lib.handle(dev), _ptr(x), N, H, W, int(thresh), int(min_size), _ptr(scratch), _ptr(out), _stream(dev)))
     return out[0] if single else out
+
+
+def resize_nearest_bg(labels, items, index_pool, bg_pool, out_pool, bg_value=3):
+    """``pisto_resize_nearest_bg``: labels CUDA u8 [n,S_h,S_w]; items = list of (tile, h, w, iy_off, ix_off, bg_off, out_off);
+    index_pool CUDA int32, bg_pool CUDA u8 or None, out_pool CUDA u8 (written).  See postproc.revise_masks_to_original."""
+    dev = _dev_index(labels)
+    arr = (_lib.ResizeDesc * len(items))()
+    for d, it in zip(arr, items):
+        d.tile, d.h, d.w, d.iy_off, d.ix_off, d.bg_off, d.out_off = (int(v) for v in it)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8) if len(items) else torch.empty(0, dtype=torch.uint8)
+    ddesc = host.to(labels.device)
+    lib = _lib.load()
+    _lib.check(lib.pisto_resize_nearest_bg(_lib.handle(dev), labels.data_ptr(), int(labels.shape[0]), int(labels.shape[1]), int(labels.shape[2]),
+                                           ddesc.data_ptr(), len(items), index_pool.data_ptr(), bg_pool.data_ptr() if bg_pool is not None else None,
+                                           out_pool.data_ptr(), int(bg_value), _stream(dev)))
+    return out_pool
+

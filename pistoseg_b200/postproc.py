@@ -63,3 +63,74 @@ def revise_masks(x, label, background=None, bg_value=3):
     out = ops.fuse_argmax_confusion([x[:, 1:]], [0], (H, W), mask_mode=_lib.MASK_MULTIPLY, decide=_lib.DECIDE_RAW, present=present,
                                     bg=bg, bg_match=1, bg_label=bg_value)
     return out["labels"]
+
+
+def pil_nearest_index(n_in, n_out):
+    """Source index of every output row / column of PIL's NEAREST resize (``Image.resize`` on a mode-'P' image; Pillow
+    ``ImagingScaleAffine``): the double ``xo = 0.5 * a`` is ACCUMULATED (``xo += a``, ``a = n_in / n_out``), index = ``int(xo)``.
+    ``np.add.accumulate`` performs exactly those sequential double additions."""
+    a = n_in / n_out
+    steps = np.full(n_out, a, dtype=np.float64)
+    steps[0] = a * 0.5
+    return np.minimum(np.add.accumulate(steps).astype(np.int64), n_in - 1).astype(np.int32)
+
+
+def revise_masks_to_original(x, label, original_hw, backgrounds=None, bg_value=3):
+    """infer_revise_masks.py:137-143,152-155 for one head: ``(x * label)[:, 1:]`` -> argmax -> PIL mode-'P' resize (NEAREST) to each
+    tile's ORIGINAL ``(h, w)`` -> ``mask[background > 0] = 3`` at the original resolution (the reference applies the background
+    AFTER the resize, on the full-size ``utils.get_background`` mask).
+
+    x CUDA f32 [B,C+1,S,S]; label [B,C+1]; original_hw: list of (h, w); backgrounds: list of [h,w] uint8 arrays / tensors
+    (0 / 255) or None.  Returns a list of CUDA uint8 [h,w] tensors (views of one pooled buffer)."""
+    B = x.shape[0]
+    small = revise_masks(x, label)                      # [B,S,S] u8, background not applied yet
+    S_h, S_w = int(small.shape[1]), int(small.shape[2])
+    idx, items, off_i, off_o = [], [], 0, 0
+    for j, (h, w) in enumerate(original_hw):
+        iy, ix = pil_nearest_index(S_h, int(h)), pil_nearest_index(S_w, int(w))
+        idx += [iy, ix]
+        items.append([j, int(h), int(w), off_i, off_i + int(h), (off_o if backgrounds is not None else -1), off_o])
+        off_i += int(h) + int(w)
+        off_o += int(h) * int(w)
+    index_pool = torch.from_numpy(np.concatenate(idx)).to(x.device)
+    bg_pool = None
+    if backgrounds is not None:
+        bg_pool = torch.cat([torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).reshape(-1).to(torch.uint8).to(x.device, non_blocking=True)
+                             for b in backgrounds])
+    out_pool = torch.empty(off_o, dtype=torch.uint8, device=x.device)
+    ops.resize_nearest_bg(small, items, index_pool, bg_pool, out_pool, bg_value)
+    return [out_pool[it[6]:it[6] + it[1] * it[2]].view(it[1], it[2]) for it in items]
+
+
+WSSS4LUAD_PALETTE = [0, 64, 128, 64, 128, 0, 243, 152, 0, 255, 255, 255] + [0] * 252 * 3   # infer_revise_masks.py:150
+BCSS_PALETTE = [255, 0, 0, 0, 255, 0, 0, 0, 255, 153, 0, 255, 255, 255, 255]                # infer_revise_masks.py:182-187
+
+
+def revise_masks_to_png(heads, label, names, original_hw, save_dir, backgrounds=None, dataset="wsss4luad", pool=None):
+    """The saving half of infer_revise_masks.py:145-206: for every head (``{'pmask': x, 'pcam': x, 'cam': x}``) writes
+    ``<save_dir>/refine/<head>/<name>.png`` -- mode 'P', the dataset's palette, original size; wsss4luad also overwrites the
+    background.  PNG encoding stays on the host (threaded through ``io.AsyncWriter`` when ``pool`` is given)."""
+    import os
+    from PIL import Image
+    wsss = dataset == "wsss4luad"
+    palette = WSSS4LUAD_PALETTE if wsss else BCSS_PALETTE
+    written = []
+    for head, x in heads.items():
+        d = os.path.join(save_dir, "refine", head)
+        os.makedirs(d, exist_ok=True)
+        masks = revise_masks_to_original(x, label, original_hw, backgrounds if wsss else None)
+        for name, m in zip(names, masks):
+            arr = m.cpu().numpy()
+            path = os.path.join(d, name + ".png")
+
+            def save(arr=arr, path=path):
+                im = Image.fromarray(np.uint8(arr), mode="P")
+                im.putpalette(palette)
+                im.save(path)
+            if pool is not None:
+                pool.submit(save)
+            else:
+                save()
+            written.append(path)
+    return written
+

@@ -10,6 +10,12 @@ What is executed:
   * torch.nn.functional.interpolate (what interpolate_tensor calls)                             -> bilinear.npz
   * cv2.flip / cv2.warpAffine / cv2.getRotationMatrix2D / cv2.copyMakeBorder through oracle.mosaic(use_cv2=True)
     (albumentations itself is not installed: the plan -> pixels contract is pinned, not its RNG)  -> mosaic.npz
+  * the test loop + big-mask fusion + report of /root/reference/segmentation_test.py:125-227, cut out as TEXT and executed
+    with a stub model / DataLoader, real PIL files in a temporary directory and `.cuda()` as a no-op          -> bigmask.npz
+  * the image loop of /root/reference/OEEM/classification/prepare_seg_inputs.py:81-138 (stub `net_cam`), with the tile
+    positions from `online_cut_patches` / `multiscale_online_crop` cut out of utils/pyutils.py with `ast`     -> oeem.npz
+  * the per-batch post-processing of /root/reference/infer_revise_masks.py:137-157 (argmax -> PIL P-mode resize ->
+    background at the original resolution), stub `utils.get_background`                                       -> revise.npz
 """
 import ast
 import importlib.util
@@ -145,8 +151,219 @@ def golden_mosaic():
     np.savez_compressed(os.path.join(HERE, "mosaic.npz"), **out)
 
 
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference SCRIPT bodies: cut out as text, dedented, executed with stubs for what is not installed / not a file here
+# ------------------------------------------------------------------------------------------------------------------
+import contextlib
+import io
+import tempfile
+import textwrap
+import types
+
+from PIL import Image
+
+
+def ref_lines(path, first, last):
+    """Lines first..last (1-based, inclusive) of a reference file, dedented."""
+    lines = open(path).read().split("\n")[first - 1:last]
+    return textwrap.dedent("\n".join(lines))
+
+
+@contextlib.contextmanager
+def cuda_is_a_noop():
+    old = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = old
+
+
+def golden_bigmask():
+    """segmentation_test.py:125-227 (wsss4luad branch): tile loop with patch-level mIoU, per-(image, scale) overlap-add of softmax
+    scores, float64 resize to the image, mean over scales, big-mask mIoU, argmax + background, mode-P PNG, report lines."""
+    path = os.path.join(REF, "segmentation_test.py")
+    src = open(path).read().split("\n")
+    first = next(i for i, l in enumerate(src) if l.strip() == "model.eval()") + 1
+    last = next(i for i, l in enumerate(src) if "MosaSegmentationic Test" in l) + 1
+    body = ref_lines(path, first, last)
+    loss = load_ref_loss()
+    interp = load_ref_functions(path, {"interpolate_tensor"})["interpolate_tensor"]
+    g = torch.Generator().manual_seed(505)
+    rng = np.random.default_rng(505)
+    P, stride, scales = 32, 24, [1.0, 1.25, 1.5]
+    images = {"00": (70, 85), "01": (93, 61)}  # (h, w)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "img")); os.makedirs(os.path.join(tmp, "mask")); os.makedirs(os.path.join(tmp, "out", "mask"))
+        gts = {}
+        for k, (h, w) in images.items():
+            Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(os.path.join(tmp, "img", k + ".png"))
+            gt = rng.integers(0, 3, (h // 8 + 1, w // 8 + 1)).repeat(8, 0).repeat(8, 1)[:h, :w].astype(np.uint8)
+            gt[rng.random((h, w)) < 0.1] = 3
+            gts[k] = gt
+            Image.fromarray(gt).save(os.path.join(tmp, "mask", k + ".png"))
+        tiles = []  # (name, logits [3,P,P], mask [P,P], original_h, original_w)
+        for k, (h, w) in images.items():
+            for s in scales:
+                hs, ws = int(h * s), int(w * s)
+                ys = sorted(set(list(range(0, max(hs - P, 0) + 1, stride)) + [max(hs - P, 0)]))
+                xs = sorted(set(list(range(0, max(ws - P, 0) + 1, stride)) + [max(ws - P, 0)]))
+                for y in ys:
+                    for x in xs:
+                        oh, ow = min(P, hs - y), min(P, ws - x)
+                        logit = torch.randn((3, P, P), generator=g) * 2
+                        msk = torch.randint(0, 4, (P, P), generator=g)
+                        tiles.append((f"{k}_{s}_{y}_{x}-[1, 1, 1].png", logit, msk, oh, ow))
+        # dataset order (image-major): the reference's second loop reuses the (h, w) of the last NEW image it met, so the keys
+        # of one image must be adjacent (segmentation_test.py:190-197) -- as they are with the unshuffled DataLoader
+        B = 7
+        batches, outputs = [], []
+        for b0 in range(0, len(tiles), B):
+            chunk = tiles[b0:b0 + B]
+            logits = torch.stack([t[1] for t in chunk]); masks = torch.stack([t[2] for t in chunk])
+            batches.append((logits.clone(), masks, [t[0] for t in chunk], [t[3] for t in chunk], [t[4] for t in chunk]))
+            outputs.append(logits)
+        calls = iter(outputs)
+        log_lines = []
+        ns = {"torch": torch, "np": np, "F": F, "os": os, "Image": Image, "tqdm": (lambda x: x), "interpolate_tensor": interp, "mIoUMask": loss.mIoUMask,
+              "args": types.SimpleNamespace(dataset="wsss4luad", test_data=os.path.join(tmp, "test"), save_dir=os.path.join(tmp, "out")),
+              "model": types.SimpleNamespace(eval=lambda: None), "test_dataloader": batches, "test_iou": loss.mIoUMask(num_classes=3),
+              "pred_big_mask_dict_ms": {}, "cnt_big_mask_dict_ms": {}, "pred_big_mask_dict": {}, "cnt_big_mask_dict": {},
+              "logging": types.SimpleNamespace(critical=log_lines.append)}
+        model = lambda image_batch: next(calls)
+        model.eval = lambda: None
+        ns["model"] = model
+        stdout = io.StringIO()
+        with cuda_is_a_noop(), contextlib.redirect_stdout(stdout):
+            exec(compile(body, path, "exec"), ns)
+        out = {"names": np.array([t[0] for t in tiles]), "logits": torch.stack([t[1] for t in tiles]).numpy(),
+               "masks": torch.stack([t[2] for t in tiles]).numpy().astype(np.uint8),
+               "orig_hw": np.array([[t[3], t[4]] for t in tiles]), "scales": np.array(scales), "batch": np.array(B),
+               "patch_cm": ns["test_iou"].confusion_matrix.copy(), "big_cm": ns["big_mask_iou"].confusion_matrix.copy(),
+               "log": np.array(log_lines), "stdout": np.array(stdout.getvalue())}
+        for k in images:
+            out[f"gt_{k}"] = gts[k]
+            out[f"fused_{k}"] = ns["pred_big_mask_dict"][k]            # [h, w, 3] float64, mean over scales
+            png = Image.open(os.path.join(tmp, "out", "mask", k + ".png"))
+            out[f"png_{k}"] = np.array(png); out[f"png_mode_{k}"] = np.array(png.mode); out[f"palette_{k}"] = np.array(png.getpalette()[:12])
+    np.savez_compressed(os.path.join(HERE, "bigmask.npz"), **out)
+
+
+def load_ref_tiling():
+    """online_cut_patches / multiscale_online_crop of OEEM/classification/utils/pyutils.py (the module itself imports skimage / png)."""
+    path = os.path.join(REF, "OEEM", "classification", "utils", "pyutils.py")
+    tree = ast.parse(open(path).read())
+    ns = {"np": np, "Image": Image}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("online_cut_patches", "multiscale_online_crop"):
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns
+
+
+def golden_oeem():
+    """prepare_seg_inputs.py:81-138 for two images; tile positions from the reference's own multiscale_online_crop."""
+    path = os.path.join(REF, "OEEM", "classification", "prepare_seg_inputs.py")
+    src = open(path).read().split("\n")
+    first = next(i for i, l in enumerate(src) if l.strip() == "with torch.no_grad():") + 1
+    last = next(i for i, l in enumerate(src) if "np.save(f'{train_pseudo_mask_path}" in l) + 1
+    body = ref_lines(path, first, last)
+    til = load_ref_tiling()
+    g = torch.Generator().manual_seed(606)
+    rng = np.random.default_rng(606)
+    side, stride, scales, C, bs = 32, 20, [1, 1.25, 1.5, 2], 3, 5
+    out = {"side": np.array(side), "stride": np.array(stride), "scales": np.array(scales, dtype=np.float64), "batch": np.array(bs)}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "img")); os.makedirs(os.path.join(tmp, "out"))
+        loader, cams_all = [], []
+        for name, (w, h) in (("a.png", (53, 70)), ("b.png", (28, 45))):  # reference naming: w = rows, h = cols of the array
+            img = rng.integers(0, 256, (w, h, 3), dtype=np.uint8)
+            Image.fromarray(img).save(os.path.join(tmp, "img", name))
+            im_lists, pos_lists = til["multiscale_online_crop"](img, side, stride, scales)
+            scaled_im_list = [[torch.zeros((1, 3, 4, 4)) for _ in l] for l in im_lists]   # the network input is irrelevant: forward_cam is a stub
+            loader.append(([name], scaled_im_list, pos_lists, scales, [torch.tensor([1, 0, 1])]))
+            out[f"{name}_wh"] = np.array([w, h])
+            for s, pl in enumerate(pos_lists):
+                cams = torch.randn((len(pl), C, 4, 4), generator=g) * 2
+                cams_all.append(cams)
+                out[f"{name}_pos{s}"] = np.array(pl, dtype=np.int64).reshape(-1, 2)
+                out[f"{name}_cam{s}"] = cams.numpy()
+        # forward_cam is called once per batch of `bs` tiles, scale by scale, image by image: hand the stored CAMs out in that order
+        queue = [c for cams in cams_all for c in torch.split(cams, bs)]
+        it = iter(queue)
+        net_cam = types.SimpleNamespace(module=types.SimpleNamespace(forward_cam=lambda ims: next(it)))
+        ns = {"torch": torch, "np": np, "F": F, "Image": Image, "tqdm": (lambda x: x), "dataLoader": loader, "net_cam": net_cam,
+              "data_path_name": os.path.join(tmp, "img"), "num_of_class": C, "side_length": side, "batch_size": bs,
+              "train_pseudo_mask_path": os.path.join(tmp, "out")}
+        with cuda_is_a_noop():
+            exec(compile(body, path, "exec"), ns)
+        for name in ("a", "b"):
+            out[f"{name}.png_ens32"] = np.load(os.path.join(tmp, "out", name + ".npy"))
+    # tile positions of online_cut_patches on a grid of sizes (incl. smaller than the tile, exact multiples, remainders)
+    cases = [(10, 10), (32, 32), (33, 40), (64, 52), (70, 53), (100, 131), (32, 95), (31, 96)]
+    out["tiling_cases"] = np.array(cases)
+    for i, (h, w) in enumerate(cases):
+        _, pos = til["online_cut_patches"](np.zeros((h, w, 3), np.uint8), side, stride)
+        out[f"tiling_pos{i}"] = np.array(pos, dtype=np.int64).reshape(-1, 2)
+    np.savez_compressed(os.path.join(HERE, "oeem.npz"), **out)
+
+
+def golden_revise():
+    """infer_revise_masks.py:137-157: (x * label)[:, 1:] -> argmax -> PIL mode-P resize to the original (w, h) -> [background > 0] = 3,
+    for the three heads."""
+    path = os.path.join(REF, "infer_revise_masks.py")
+    src = open(path).read().split("\n")
+    first = next(i for i, l in enumerate(src) if "pmask_rv = (pmask_rv * label)[:, 1:, :, :]" in l) + 1
+    last = next(i for i, l in enumerate(src) if "pmask_rv_mask.putpalette(palette)" in l) + 1
+    body = ref_lines(path, first, last)
+    g = torch.Generator().manual_seed(707)
+    rng = np.random.default_rng(707)
+    B, C, S = 5, 3, 48
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        names, bgs = [], {}
+        sizes = [(60, 75), (48, 48), (31, 52), (90, 64), (47, 49)]  # original (h, w): up- and down-sampling of the 48 x 48 masks
+        for i, (h, w) in enumerate(sizes):
+            Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(os.path.join(tmp, f"t{i}.png"))
+            names.append(f"t{i}")
+            bgs[(h, w, i)] = ((rng.random((h, w)) < 0.2) * 255).astype(np.uint8)
+        heads = {k: torch.randn((B, C + 1, S, S), generator=g) * 2 for k in ("pmask_rv", "pcam_rv", "cam_rv")}
+        heads["pcam_rv"][1] = -heads["pcam_rv"][1].abs()  # all scores negative: an absent class (exactly 0 after the multiply) wins
+        lab = torch.tensor([[1, 1, 0], [0, 1, 0], [1, 1, 1], [1, 0, 1], [0, 0, 1]], dtype=torch.float32)
+        label = torch.cat((torch.ones((B, 1)), lab), dim=1).unsqueeze(2).unsqueeze(3)
+        bg_iter = iter(bgs.values())
+        saved = {}
+
+        class Capture(dict):  # the loop body rebinds pmask_rv_mask per tile: keep every final value
+            def __setitem__(self, k, v):
+                if k == "pmask_rv_mask" and isinstance(v, Image.Image):
+                    saved.setdefault(k, []).append(v)
+                super().__setitem__(k, v)
+        ns = Capture({"torch": torch, "np": np, "Image": Image, "os": os, "name_batch": names, "label": label,
+                      "args": types.SimpleNamespace(train_dir=tmp, dataset="wsss4luad", checkpoint=os.path.join(tmp, "ckpt", "x.ckpt")),
+                      "utils": types.SimpleNamespace(get_background=lambda img: next(bg_iter)), **{k: v.clone() for k, v in heads.items()}})
+        # the cut ends inside the per-tile loop, right after putpalette: the body is complete statements up to there
+        exec(compile(body, path, "exec"), ns)
+        for k, v in heads.items():
+            out[k] = v.numpy()
+        out["label"] = label.numpy()[:, :, 0, 0]
+        out["sizes"] = np.array(sizes)
+        for i, key in enumerate(bgs):
+            out[f"background{i}"] = bgs[key]
+        # saved holds, per tile, first the resized-array wrapped image (before the bg rebinding it is an ndarray -> not captured) -- take the last Image per tile
+        finals = saved["pmask_rv_mask"]
+        assert len(finals) == B, len(finals)
+        for i, im in enumerate(finals):
+            out[f"pmask_png{i}"] = np.array(im); out[f"pmask_mode{i}"] = np.array(im.mode)
+        for k in ("pmask_rv_masks", "pcam_rv_masks", "cam_rv_masks"):
+            out[k] = np.asarray(ns[k]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "revise.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_miou(); golden_pmask(); golden_bilinear(); golden_mosaic()
+    golden_bigmask(); golden_oeem(); golden_revise()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

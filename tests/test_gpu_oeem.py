@@ -9,26 +9,11 @@ from pistoseg_b200 import oeem
 pytestmark = pytest.mark.gpu
 
 
-def _literal_positions(h, w, im_size, stride):
-    """pyutils.py:27-46, literally."""
-    if h < im_size:
-        h_ = np.array([0])
-    else:
-        h_ = np.arange(0, h - im_size + 1, stride)
-        if h % stride != 0:
-            h_ = np.append(h_, h - im_size)
-    if w < im_size:
-        w_ = np.array([0])
-    else:
-        w_ = np.arange(0, w - im_size + 1, stride)
-        if w % stride != 0:
-            w_ = np.append(w_, w - im_size)
-    return [(int(i), int(j)) for i in h_ for j in w_]
-
-
 def _case(g, wh, scales, C=3, side=224, stride=74):
     w, h = wh  # the reference's (rows, cols)
-    pos = [_literal_positions(int(w * s), int(h * s), side, stride) for s in scales]
+    # tile positions: the product's host code, pinned against the reference's own online_cut_patches by
+    # tests/test_oracle_golden.py::test_tiling_positions_match_the_reference_function (fixture oeem.npz)
+    pos = [oeem.online_cut_positions(int(w * s), int(h * s), side, stride) for s in scales]
     cams = [torch.randn((len(p), C, 28, 28), generator=g) * 2 for p in pos]
     return cams, pos
 
@@ -38,7 +23,6 @@ def test_cam_ensemble_32_and_labels(cuda, wh):
     g = torch.Generator().manual_seed(wh[0] + wh[1])
     scales = [1, 1.25, 1.5, 1.75, 2]                       # configuration_wsss4luad.yml:8
     cams, pos = _case(g, wh, scales)
-    assert pos == [oeem.online_cut_positions(int(wh[0] * s), int(wh[1] * s), 224, 74) for s in scales]
     ref = ostitch.cam_ensemble(cams, pos, scales, wh)
     got = oeem.cam_ensemble([c.to(cuda) for c in cams], pos, scales, wh)
     # no softmax anywhere on this path: f32 upsample and f64 sums are evaluated in the reference's order -> bit-exact
@@ -57,3 +41,23 @@ def test_small_image_uses_the_scaled_size(cuda):
     ref = ostitch.cam_ensemble(cams, pos, scales, wh)
     got = oeem.cam_ensemble([c.to(cuda) for c in cams], pos, scales, wh)
     assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_ensemble_matches_the_reference_script_fixture(cuda):
+    """GPU path vs prepare_seg_inputs.py:81-138 executed on synthetic CAMs (tests/golden/oeem.npz): f32 upsample of the CAMs, f64
+    overlap-add per scale, f64 resize, mean over scales, f64 resize to 32 x 32."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "oeem.npz"))
+    scales, side, stride = [float(s) for s in z["scales"]], int(z["side"]), int(z["stride"])
+    for name in ("a.png", "b.png"):
+        wh = tuple(int(v) for v in z[f"{name}_wh"])
+        cams = [torch.from_numpy(z[f"{name}_cam{s}"]).to(cuda) for s in range(len(scales))]
+        pos = oeem.multiscale_positions(wh[0], wh[1], side, stride, scales)
+        for s, p in enumerate(pos):
+            assert p == [tuple(int(v) for v in q) for q in z[f"{name}_pos{s}"]]
+        got = oeem.ensemble_32(cams, pos, scales, wh, side=side).cpu().numpy()
+        ref = z[f"{name}_ens32"]
+        # the fixture's 4 x 4 CAMs go through ATen's scalar CPU bilinear (no fma); the CUDA kernel equals ATen's vectorised / CUDA path
+        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+        assert np.array_equal(got, ostitch.cam_to_32(ostitch.cam_ensemble([c.cpu() for c in cams], pos, scales, wh, side=side)))
+

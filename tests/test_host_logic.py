@@ -32,6 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.MosaicQuad) == 64
     assert ctypes.sizeof(_lib.MosaicPlan) == 16 + 4 * 64
     assert ctypes.sizeof(_lib.MosaicCell) == 8
+    assert ctypes.sizeof(_lib.ResizeDesc) == 4 * 4 + 4 * 8
 
 
 def test_no_cpu_fallback_without_device():
