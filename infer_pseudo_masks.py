@@ -64,6 +64,11 @@ def main(args, model=None, dataset=None, original_size=None):
     device = torch.device("cuda", args.gpus if args.gpus is not None else 0)
     if model is None:
         from models.mosaic_module import MosaicModule     # reference module (backbone stays in PyTorch)
+        import argparse
+        try:  # torch >= 2.6: Lightning's internal torch.load runs with weights_only=True and must be allowed the checkpoint's Namespace
+            torch.serialization.add_safe_globals([argparse.Namespace])
+        except AttributeError:
+            pass
         model = MosaicModule.load_from_checkpoint(args.checkpoint).cuda(device)
     if dataset is None:
         from dataset import TrainDataset                   # reference module

@@ -33,8 +33,7 @@ extern "C" int pisto_create(pisto_handle_t* out, int device) {
     pisto_set_error("pisto_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
     return PISTO_ERR_NO_DEVICE;
   }
-  pisto_ctx* c = new pisto_ctx();
-  memset(c, 0, sizeof(*c));
+  pisto_ctx* c = new pisto_ctx();  // value-initialised: every member zero (the atomics included)
   c->device = device;
   c->sm_count = p.multiProcessorCount;
   c->smem_optin = (int)p.sharedMemPerBlockOptin;
@@ -51,6 +50,8 @@ extern "C" int pisto_create(pisto_handle_t* out, int device) {
 extern "C" int pisto_destroy(pisto_handle_t h) {
   if (!h) return PISTO_OK;
   if (h->sched) { cudaSetDevice(h->device); cudaFree(h->sched); }
+  for (int i = 0; i < PISTO_SCHED_SLOTS; i++)
+    if (h->sched_done[i]) cudaEventDestroy(h->sched_done[i]);
   if (h->pipe_ready) {
     cudaSetDevice(h->device);
     for (int i = 0; i < PISTO_PIPE_SLOTS; i++) {
@@ -65,4 +66,24 @@ extern "C" int pisto_destroy(pisto_handle_t h) {
   return PISTO_OK;
 }
 
-extern "C" int64_t pisto_launch_count(pisto_handle_t h) { return h ? h->launches : 0; }
+extern "C" int64_t pisto_launch_count(pisto_handle_t h) { return h ? (int64_t)h->launches.load() : 0; }
+
+int pisto_sched_acquire(pisto_ctx* h, cudaStream_t st, int** counter, int* slot) {
+  const int s = (int)(h->sched_next.fetch_add(1u) % PISTO_SCHED_SLOTS);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PISTO_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap == cudaStreamCaptureStatusNone && h->sched_done[s]) PISTO_CUDA(cudaStreamWaitEvent(st, h->sched_done[s], 0));
+  *counter = h->sched + s;
+  *slot = s;
+  PISTO_CUDA(cudaMemsetAsync(*counter, 0, sizeof(int), st));
+  return PISTO_OK;
+}
+
+int pisto_sched_release(pisto_ctx* h, cudaStream_t st, int slot) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PISTO_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return PISTO_OK;
+  if (!h->sched_done[slot]) PISTO_CUDA(cudaEventCreateWithFlags(&h->sched_done[slot], cudaEventDisableTiming));
+  PISTO_CUDA(cudaEventRecord(h->sched_done[slot], st));
+  return PISTO_OK;
+}

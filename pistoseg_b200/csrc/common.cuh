@@ -8,6 +8,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -22,9 +24,10 @@ struct pisto_ctx {
   int device;
   int sm_count;
   int smem_optin;   // max dynamic shared memory per block
-  long long launches;
+  std::atomic<long long> launches;
   int* sched;       // ring of device tile counters for the persistent kernels' dynamic scheduler
-  unsigned int sched_next;
+  std::atomic<unsigned int> sched_next;
+  cudaEvent_t sched_done[PISTO_SCHED_SLOTS];  // recorded after the kernel that used slot s: the next user of s waits for it (any stream)
   // resources of the host-buffer (e2e) pipeline, created lazily
   cudaStream_t pipe_stream[PISTO_PIPE_SLOTS];
   cudaEvent_t pipe_done[PISTO_PIPE_SLOTS];
@@ -36,6 +39,13 @@ struct pisto_ctx {
 };
 
 void pisto_set_error(const char* fmt, ...);
+
+// A persistent kernel's dynamic tile scheduler needs a zeroed device counter for the duration of the launch.  Counters come from a
+// ring; a slot is re-armed (memset on the launch stream) only after the kernel that used it last has finished, on WHATEVER stream
+// that was: the launch stream first waits for the slot's event.  Callers may therefore drive one handle from several streams or
+// threads (slot choice and launch count are atomic); during stream capture the events are left alone (the graph orders its nodes).
+int pisto_sched_acquire(pisto_ctx* h, cudaStream_t st, int** counter, int* slot);
+int pisto_sched_release(pisto_ctx* h, cudaStream_t st, int slot);
 
 #define PISTO_CUDA(call)                                                                              \
   do {                                                                                                \

@@ -1226,13 +1226,14 @@ int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
     }
   }
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
-  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  int sched_slot = 0;
+  { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
   const int slots = h->sm_count * ctas;
   const int grid = p.N < slots ? p.N : slots;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
+  { const int rc = pisto_sched_release(h, st, sched_slot); if (rc != PISTO_OK) return rc; }
   *launched = true;
   return PISTO_OK;
 }

@@ -1496,13 +1496,14 @@ int launch_duo(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launche
   if (!make_duo_geom<C, G, VPG>(h, p, &g)) return PISTO_OK;
   auto kern = fuse_duo_kernel<C, G, VPG, F>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
-  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  int sched_slot = 0;
+  { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
   const int slots = 2 * h->sm_count;
   const int grid = p.N < slots ? p.N : slots;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
+  { const int rc = pisto_sched_release(h, st, sched_slot); if (rc != PISTO_OK) return rc; }
   *launched = true;
   return PISTO_OK;
 }
@@ -1513,12 +1514,13 @@ int launch_narrow(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   if (!make_static_geom<C, G, VPG>(h, p, NB, &g, 1) || g.threads > kSNarrowThreads) return PISTO_OK;
   auto kern = fuse_narrow_kernel<C, G, VPG, F, NB>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
-  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  int sched_slot = 0;
+  { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
   const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
+  { const int rc = pisto_sched_release(h, st, sched_slot); if (rc != PISTO_OK) return rc; }
   *launched = true;
   return PISTO_OK;
 }
@@ -1529,12 +1531,13 @@ int launch_static(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   if (!make_static_geom<C, G, VPG>(h, p, NB, &g)) return PISTO_OK;
   auto kern = fuse_static_kernel<C, G, VPG, F, NB>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
-  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  int sched_slot = 0;
+  { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
   const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
+  { const int rc = pisto_sched_release(h, st, sched_slot); if (rc != PISTO_OK) return rc; }
   *launched = true;
   return PISTO_OK;
 }

@@ -585,12 +585,13 @@ int launch_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched
   if (!make_geom(h, p, &g)) return PISTO_OK;  // not launched: caller falls back
   auto kern = fuse_stream_kernel<C, V, PROB, F, PAIRS>;
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-  g.counter = h->sched + (h->sched_next++ % PISTO_SCHED_SLOTS);
-  PISTO_CUDA(cudaMemsetAsync(g.counter, 0, sizeof(int), st));
+  int sched_slot = 0;
+  { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
   const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
   PISTO_CUDA(cudaGetLastError());
+  { const int rc = pisto_sched_release(h, st, sched_slot); if (rc != PISTO_OK) return rc; }
   *launched = true;
   return PISTO_OK;
 }

@@ -47,8 +47,11 @@ class mIoUMask(torch.nn.Module):
         """Sum the device accumulator over the ranks of a torch.distributed process group (one NCCL all-reduce of
         C*C int64 values); exact, independent of the number of ranks."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and self._conf is not None:
-            dist.all_reduce(self._conf, op=dist.ReduceOp.SUM, group=group)
+        if dist.is_available() and dist.is_initialized():
+            # every rank takes part, also one whose shard was empty and never created its accumulator (else the others would
+            # block in the collective for ever)
+            conf = self._conf if self._conf is not None else self._acc(self._device or torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(conf, op=dist.ReduceOp.SUM, group=group)
 
     # ---- reference API ----------------------------------------------------------------------------------------------
     def _generate_matrix(self, pre_image, gt_image):

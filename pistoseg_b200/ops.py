@@ -230,6 +230,14 @@ def stitch_accumulate(tiles, pos, canvas, count, softmax=True):
     n, C_, th, tw = tiles.shape
     if canvas.dtype != torch.float64 or count.dtype != torch.float64 or not canvas.is_contiguous() or not count.is_contiguous():
         raise _lib.PistoError("canvas / count must be contiguous float64 CUDA tensors")
+    if pos.shape[0] != n:
+        raise _lib.PistoError(f"stitch_accumulate: {pos.shape[0]} positions for {n} tiles")
+    if n:
+        # a crop larger than the tile would read the next tile (or past the buffer); the reference's numpy slicing cannot do that
+        lo = pos.min(dim=0).values.tolist()
+        hi = pos.max(dim=0).values.tolist()
+        if lo[0] < 0 or lo[1] < 0 or lo[2] < 1 or lo[3] < 1 or hi[2] > th or hi[3] > tw:
+            raise _lib.PistoError(f"stitch_accumulate: positions need y, x >= 0 and 1 <= crop_h <= {th}, 1 <= crop_w <= {tw}; got min {lo}, max {hi}")
     lib = _lib.load()
     _lib.check(lib.pisto_stitch_accumulate(_lib.handle(dev), _ptr(tiles), _ptr(pos), n, C_, th, tw, int(bool(softmax)), _ptr(canvas),
                                            _ptr(count), canvas.shape[-2], canvas.shape[-1], _stream(dev)))

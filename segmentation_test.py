@@ -67,6 +67,17 @@ def report(test_iou, big_iou, dataset):
         logging.critical(f"Segmentation Test - Test tissue IoU (big mask): {test_iou.Tissue_Intersection_over_Union()}")
 
 
+def _trust_local_checkpoints():
+    """torch >= 2.6 unpickles with weights_only=True by default and refuses the argparse.Namespace a Lightning checkpoint of this
+    project carries (hyper_parameters['args']).  The checkpoints are the user's own training output, as in the reference
+    (segmentation_test.py:94,106): allow-list the Namespace so that Lightning's internal torch.load works too."""
+    import argparse
+    try:
+        torch.serialization.add_safe_globals([argparse.Namespace])
+    except AttributeError:  # older torch: nothing to do
+        pass
+
+
 def main(args, model=None, dataset=None, image_size=None, load_gt=None):
     """model / dataset / image_size(image_idx)->(w,h) / load_gt(image_idx)->uint8 [h,w] can be injected; the defaults
     are the reference's SegmentationModule checkpoint, TestDataset and the PNGs next to the patch directory."""
@@ -77,7 +88,8 @@ def main(args, model=None, dataset=None, image_size=None, load_gt=None):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
     if model is None:
-        lib = torch.load(args.checkpoint, map_location="cpu")
+        _trust_local_checkpoints()
+        lib = torch.load(args.checkpoint, map_location="cpu", weights_only=False)  # a Lightning checkpoint: hyper_parameters['args'] is an argparse.Namespace
         model_args = lib["hyper_parameters"]["args"]
         for k, v in vars(args).items():
             setattr(model_args, k, v)

@@ -172,3 +172,64 @@ def test_function_level_dropins(cuda):
         assert np.abs(np.asarray(ent, np.float32) - z[f"entropy{i}"]).max() <= 2e-5
         assert np.array_equal(logit.cpu().numpy(), z[f"mutated{i}"]), "the reference's in-place -1e10 fill must be reproduced"
         i += 1
+
+
+def test_segmentation_test_loads_a_lightning_style_checkpoint(cuda, tmp_path, monkeypatch):
+    """The script's DEFAULT path (no injected model / dataset, run.sh:64): torch.load of a checkpoint whose
+    hyper_parameters['args'] is an argparse.Namespace -- refused by torch >= 2.6 unless the script opts out of weights_only --
+    then SegmentationModule.load_from_checkpoint and TestDataset from the (here: stand-in) reference modules."""
+    import argparse
+    import sys
+    import segmentation_test as script
+    P, C = 48, 3
+    ds = PatchDataset(P, C, seed=21)
+    ckpt_dir = tmp_path / "logs"
+    ckpt_dir.mkdir()
+    ckpt = ckpt_dir / "epoch=03-val_iou=0.5.ckpt"
+    hp = argparse.Namespace(dataset="wsss4luad", lr=0.1, arch="stub")
+    torch.save({"hyper_parameters": {"args": hp}, "state_dict": StubBackbone(C, P, seed=22).state_dict()}, ckpt)
+
+    class SegmentationModule:
+        @staticmethod
+        def load_from_checkpoint(path, args=None):
+            blob = torch.load(path, map_location="cpu")      # what Lightning does internally: default weights_only
+            m = StubBackbone(C, P, seed=0)
+            m.load_state_dict(blob["state_dict"])
+            return m
+
+    monkeypatch.setitem(sys.modules, "models", types.ModuleType("models"))
+    mod = types.ModuleType("models.segmentation_module"); mod.SegmentationModule = SegmentationModule
+    monkeypatch.setitem(sys.modules, "models.segmentation_module", mod)
+    dmod = types.ModuleType("dataset"); dmod.TestDataset = lambda args: ds
+    monkeypatch.setitem(sys.modules, "dataset", dmod)
+    data = tmp_path / "data"
+    (data / "img").mkdir(parents=True); (data / "mask").mkdir()
+    for idx, (h, w) in ds.sizes.items():
+        Image.fromarray(np.zeros((h, w, 3), np.uint8)).save(data / "img" / f"{idx}.png")
+        Image.fromarray(ds.gt[idx]).save(data / "mask" / f"{idx}.png")
+    args = argparse.Namespace(dataset="wsss4luad", checkpoint=str(ckpt), patch_size=P, test_data=str(data / "patches"), batch_size=7, gpus=[0],
+                              num_workers=0, pin_memory=False, save_dir=str(ckpt_dir / "test"))
+    test_iou, big_iou = script.main(args)
+    assert big_iou.confusion_matrix.sum() == sum(int((g < 3).sum()) for g in ds.gt.values())
+    assert (ckpt_dir / "test" / "mask" / "00.png").exists()
+
+
+def test_all_reduce_with_an_empty_shard_creates_the_accumulator(cuda):
+    """A rank whose shard is empty must still own a matrix to put into the collective (metrics.mIoUMask.all_reduce)."""
+    from pistoseg_b200.metrics import mIoUMask
+    m = mIoUMask(num_classes=3, device=cuda)
+    assert m._conf is None
+    m.all_reduce()                      # not distributed here: must be a no-op that does not fail
+    assert float(m.confusion_matrix.sum()) == 0.0
+
+
+def test_stitch_rejects_crops_larger_than_the_tile(cuda):
+    from pistoseg_b200 import ops
+    from pistoseg_b200._lib import PistoError
+    tiles = torch.zeros((2, 3, 8, 8), device=cuda)
+    canvas = torch.zeros((3, 16, 16), dtype=torch.float64, device=cuda); count = torch.zeros((16, 16), dtype=torch.float64, device=cuda)
+    for bad in ([[0, 0, 9, 8], [0, 0, 8, 8]], [[0, 0, 8, 12], [0, 0, 8, 8]], [[-1, 0, 8, 8], [0, 0, 8, 8]], [[0, 0, 8, 8]]):
+        with pytest.raises(PistoError):
+            ops.stitch_accumulate(tiles, bad, canvas, count)
+    ops.stitch_accumulate(tiles, [[0, 0, 8, 8], [8, 8, 5, 3]], canvas, count)
+
