@@ -76,6 +76,11 @@ int pisto_create(pisto_handle_t* out, int device);
 int pisto_destroy(pisto_handle_t h);
 /* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t pisto_launch_count(pisto_handle_t h);
+/* Data-dependence record of the filtered fusion kernels (the label fast path trusts a pixel only above an error-bound margin and
+ * re-evaluates the others exactly): out_host[1] = multi-label tiles processed, out_host[2] = pixels that went through the exact
+ * pass, out_host[3] = tiles evaluated exactly as a whole (queue overflow, non-finite / absurd logits, empty presence vector);
+ * out_host[0] is reserved.  Synchronises the device; reset != 0 zeroes the counters afterwards. */
+int pisto_filter_stats(pisto_handle_t h, unsigned long long* out_host /* [4] */, int reset);
 
 /* -------------------------------------------------------------------------------------------------- */
 /* confusion matrix: replaces mIoUMask._generate_matrix / add_batch (loss.py:17-31)                   */

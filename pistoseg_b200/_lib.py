@@ -69,6 +69,7 @@ SYMBOLS = {
     "pisto_create": (_i, [C.POINTER(_vp), _i]),
     "pisto_destroy": (_i, [_vp]),
     "pisto_launch_count": (_i64, [_vp]),
+    "pisto_filter_stats": (_i, [_vp, _vp, _i]),
     "pisto_confusion_accumulate": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "pisto_fuse_argmax_confusion": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _vp]),
     "pisto_fuse_argmax_confusion_host": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _i]),
@@ -140,3 +141,11 @@ def launch_count(device_index=0):
 def last_pipeline_ms(device_index=0):
     h = _handles.get(device_index)
     return float(load().pisto_last_pipeline_ms(h)) if h is not None else 0.0
+
+
+def filter_stats(device=0, reset=True):
+    """dict(multi_tiles, exact_pixels, exact_tiles) of the filtered fusion kernels since the last reset (pisto_filter_stats)."""
+    buf = (C.c_ulonglong * 4)()
+    check(load().pisto_filter_stats(handle(device), buf, int(bool(reset))))
+    return {"multi_tiles": int(buf[1]), "exact_pixels": int(buf[2]), "exact_tiles": int(buf[3])}
+

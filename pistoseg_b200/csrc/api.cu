@@ -43,6 +43,12 @@ extern "C" int pisto_create(pisto_handle_t* out, int device) {
     pisto_set_error("pisto_create: cudaMalloc failed");
     return PISTO_ERR_CUDA;
   }
+  if (cudaMalloc(&c->stats, 4 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(c->stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaFree(c->sched);
+    delete c;
+    pisto_set_error("pisto_create: cudaMalloc failed");
+    return PISTO_ERR_CUDA;
+  }
   *out = c;
   return PISTO_OK;
 }
@@ -50,6 +56,7 @@ extern "C" int pisto_create(pisto_handle_t* out, int device) {
 extern "C" int pisto_destroy(pisto_handle_t h) {
   if (!h) return PISTO_OK;
   if (h->sched) { cudaSetDevice(h->device); cudaFree(h->sched); }
+  if (h->stats) { cudaSetDevice(h->device); cudaFree(h->stats); }
   for (int i = 0; i < PISTO_SCHED_SLOTS; i++)
     if (h->sched_done[i]) cudaEventDestroy(h->sched_done[i]);
   if (h->pipe_ready) {
@@ -67,6 +74,15 @@ extern "C" int pisto_destroy(pisto_handle_t h) {
 }
 
 extern "C" int64_t pisto_launch_count(pisto_handle_t h) { return h ? (int64_t)h->launches.load() : 0; }
+
+extern "C" int pisto_filter_stats(pisto_handle_t h, unsigned long long* out_host, int reset) {
+  PISTO_REQUIRE(h && out_host, "pisto_filter_stats: NULL argument");
+  PISTO_CUDA(cudaSetDevice(h->device));
+  PISTO_CUDA(cudaDeviceSynchronize());
+  PISTO_CUDA(cudaMemcpy(out_host, h->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) PISTO_CUDA(cudaMemset(h->stats, 0, 4 * sizeof(unsigned long long)));
+  return PISTO_OK;
+}
 
 int pisto_sched_acquire(pisto_ctx* h, cudaStream_t st, int** counter, int* slot) {
   const int s = (int)(h->sched_next.fetch_add(1u) % PISTO_SCHED_SLOTS);

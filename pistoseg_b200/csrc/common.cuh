@@ -25,6 +25,7 @@ struct pisto_ctx {
   int sm_count;
   int smem_optin;   // max dynamic shared memory per block
   std::atomic<long long> launches;
+  unsigned long long* stats;  // [4] device counters of the filtered kernels: -, multi-label tiles, queued pixels, whole-tile exact fallbacks
   int* sched;       // ring of device tile counters for the persistent kernels' dynamic scheduler
   std::atomic<unsigned int> sched_next;
   cudaEvent_t sched_done[PISTO_SCHED_SLOTS];  // recorded after the kernel that used slot s: the next user of s waits for it (any stream)

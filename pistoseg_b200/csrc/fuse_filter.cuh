@@ -17,7 +17,7 @@
 //               (cfg 2, two classes present: 3 instead of 54).
 //   filter      the candidate order of (0, D_1 .. D_K) is trusted only when the best candidate leads the runner-up by
 //               more than tau = A * (2 * cE * 2^-24 + 2.5e-7) + V * 2e-6 * 1.01,  A = V * max|x| (error analysis in
-//               cE = 2 n_max + 4 G + 2 V + 16 bounds the rounding of both evaluations; the remaining
+//               cE = 2 n_max + 4 G + 2 V + 20 bounds the rounding of both evaluations; the remaining
 //               terms are the argmax(softmax(a / V)) == argmax(a) margin of common.cuh).  Then the exact fp32 sums a_c of
 //               the reference are ordered the same way with that margin and the label is the reference's, bit for bit.
 //   exact pass  pixels that fail the test (about 1e-4 of them on Gaussian logits) are queued in shared memory and, after
@@ -73,6 +73,7 @@ struct FilterGeom {
   int col4_off, col4i_off;             // 4-column tables (T4): [G][GX] float4 l1 of the thread's columns; [G][GX] u32 (4*j0 of column 0) | sel << 16
   int smem_bytes;
   int* counter;
+  unsigned long long* stats;          // [4] device counters of the handle (pisto_filter_stats) or NULL
 };
 
 struct FCtl {
@@ -886,6 +887,10 @@ __device__ __forceinline__ void fuse_filter_body(const FuseParams& p, const Filt
     // ---- exact pass: queued pixels (or the whole tile), operation by operation as the reference ----------------------
     if (multi) {
       const unsigned int nq = ctl->qcount[b];
+      if (tid == 0 && g.stats) {  // data-dependence record: queued pixels, whole-tile fallbacks (pisto_filter_stats)
+        atomicAdd(&g.stats[1], 1ull);
+        if (!exact_all && nq <= (unsigned)kFQueueCap) atomicAdd(&g.stats[2], (unsigned long long)nq); else atomicAdd(&g.stats[3], 1ull);
+      }
       if (nq > (unsigned)kFQueueCap && !exact_all) { exact_all = true; cnt_lo = cnt_hi = 0; }  // overflow: redo the whole tile
       // A queued pixel is evaluated by a whole warp: lane l computes the bilinear sample of (view l / C, class l % C), the
       // sums are then formed in view order through shuffles -- the latency of one pixel is that of one sample, and the few
@@ -1228,6 +1233,7 @@ int launch_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   int sched_slot = 0;
   { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
+  g.stats = h->stats;
   const int slots = h->sm_count * ctas;
   const int grid = p.N < slots ? p.N : slots;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);

@@ -103,6 +103,7 @@ struct StaticGeom {
   float tau_coef, tau_abs;
   int ctl_off, col4_off, col4i_off, lowtab_off, ymap_off, queue_off, lab_off, views_off, smem_bytes;
   int* counter;
+  unsigned long long* stats;          // [4] device counters of the handle (pisto_filter_stats) or NULL
 };
 
 // horizontally interpolated values of the thread's 4 columns on one map row (3 adjacent source cells at `a`)
@@ -795,6 +796,10 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
       // Pixels that failed the lead test (about 1e-4 of them on Gaussian logits) are re-evaluated exactly -- operation by
       // operation as torch does -- one pixel per warp at a time, spread over all warps.
       const unsigned int nq = ctl->qcount[b];
+      if (tid == 0 && g.stats) {  // data-dependence record: queued pixels, whole-tile fallbacks (pisto_filter_stats)
+        atomicAdd(&g.stats[1], 1ull);
+        if (!exact_all && nq <= (unsigned)kFQueueCap) atomicAdd(&g.stats[2], (unsigned long long)nq); else atomicAdd(&g.stats[3], 1ull);
+      }
       if (nq > (unsigned)kFQueueCap) exact_all = true;  // overflow: redo the whole tile
       if (!exact_all && nq) {
         for (int j = tid >> 5; j < (int)nq; j += g.cwarps) {
@@ -1259,6 +1264,10 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
       if (tid == 0) ctl->maxbits[b] = 0u;
       request_masks();
       const unsigned int nq = ctl->qcount[b];
+      if (tid == 0 && g.stats) {
+        atomicAdd(&g.stats[1], 1ull);
+        if (!exact_all && nq <= (unsigned)kDQueueCap) atomicAdd(&g.stats[2], (unsigned long long)nq); else atomicAdd(&g.stats[3], 1ull);
+      }
       if (nq > (unsigned)kDQueueCap) exact_all = true;  // overflow: redo the whole tile
       if (!exact_all && nq) {
         // queued groups, one pixel per warp at a time; the 2-bit field is patched with two word atomics (other fields of the word
@@ -1498,6 +1507,7 @@ int launch_duo(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launche
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   int sched_slot = 0;
   { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
+  g.stats = h->stats;
   const int slots = 2 * h->sm_count;
   const int grid = p.N < slots ? p.N : slots;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
@@ -1516,6 +1526,7 @@ int launch_narrow(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   int sched_slot = 0;
   { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
+  g.stats = h->stats;
   const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;
@@ -1533,6 +1544,7 @@ int launch_static(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* laun
   PISTO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
   int sched_slot = 0;
   { const int rc = pisto_sched_acquire(h, st, &g.counter, &sched_slot); if (rc != PISTO_OK) return rc; }
+  g.stats = h->stats;
   const int grid = p.N < h->sm_count ? p.N : h->sm_count;
   kern<<<grid, g.threads, g.smem_bytes, st>>>(p, g);
   h->launches++;

@@ -80,3 +80,29 @@ def cfg5(N=8, T=512, C=4, scales=(1, 1.25, 1.5, 1.75, 2)):
     views, codes = make_views(N, C, view_sizes(T, scales), 5001)
     gt = make_gt(N, T, C, 5002, ignore_frac=0.05)
     return dict(views=views, codes=codes, T=T, C=C, gt=gt, bg=None, present=None)
+
+
+def family_views(name, N, sizes, gen, dev, C=3):
+    """Input families for the data-dependence record of the filtered kernels (tests/test_gpu_filter.py, tools/bench_all.py): seeded view
+    sets generated ON the device, [N,C,h,h] per view.  gauss: i.i.d. N(0, 3^2) (the bench default); smooth: low-frequency fields (large
+    uniform regions, long class boundaries -- what a trained backbone emits); neartie / quantized / extreme: adversarial."""
+    views = []
+    for h in sizes:
+        if name == "gauss":
+            v = torch.randn((N, C, h, h), generator=gen, device=dev) * 3
+        elif name == "smooth":          # low-frequency fields + a little noise: large uniform regions, long class boundaries
+            coarse = torch.randn((N, C, 4, 4), generator=gen, device=dev) * 3
+            v = torch.nn.functional.interpolate(coarse, (h, h), mode="bilinear", align_corners=True) + torch.randn((N, C, h, h), generator=gen, device=dev) * 0.05
+        elif name == "neartie":         # classes differ by 1e-7 .. 1e-2 almost everywhere
+            base = torch.randn((N, 1, h, h), generator=gen, device=dev) * 3
+            eps = 10 ** (torch.rand((N, 1, 1, 1), generator=gen, device=dev) * 5 - 7)
+            v = base + torch.randn((N, C, h, h), generator=gen, device=dev) * eps
+        elif name == "quantized":       # multiples of 0.5: exact ties everywhere
+            v = torch.round(torch.randn((N, C, h, h), generator=gen, device=dev) * 2) / 2
+        elif name == "extreme":         # denormals, tiny and huge magnitudes per tile
+            mag = 10 ** (torch.rand((N, 1, 1, 1), generator=gen, device=dev) * 58 - 40)
+            v = torch.randn((N, C, h, h), generator=gen, device=dev) * mag
+        else:
+            raise KeyError(name)
+        views.append(v.contiguous())
+    return views

@@ -210,3 +210,44 @@ def test_full_size_runs_through_size_independent_properties(cuda):
     one = run(b3, cuda, IMPL_STREAM, decide=DECIDE_SOFTMAX, conf=ops.new_confusion(4, cuda))["conf"]
     assert torch.equal(conf, 10 * one)
     assert int(conf.sum().item()) == 10 * int((b3["gt"] < 4).sum().item())
+
+
+@pytest.mark.parametrize("family", ["gauss", "smooth", "neartie", "quantized", "extreme"])
+def test_differential_100k_tiles_filter_vs_generic(cuda, family):
+    """10^5 random tiles per run (5 input families x 20 480): the filtered kernels (automatic dispatch = the shape-specialised one) must
+    give the generic one-thread-per-pixel kernel's labels and 32x32 logits bit for bit; the fraction of pixels that needed the exact
+    pass is recorded (pisto_filter_stats)."""
+    from pistoseg_b200 import _lib
+    gen = torch.Generator(device=cuda).manual_seed(hash(family) % (2 ** 31))
+    sizes, codes = [21, 21, 28, 28, 35, 35], [0, 4, 0, 4, 0, 4]
+    chunk, rounds = 4096, 5
+    _lib.filter_stats(0, reset=True)
+    for r in range(rounds):
+        views = synthetic.family_views(family, chunk, sizes, gen, cuda)
+        present = (torch.rand((chunk, 3), generator=gen, device=cuda) < 0.6).to(torch.uint8)
+        present[:, 0] |= (present.sum(1) == 0).to(torch.uint8)        # at least one class
+        bg = (torch.rand((chunk, 224, 224), generator=gen, device=cuda) < 0.1).to(torch.uint8)
+        kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=present, bg=bg, bg_match=1, bg_label=3, lowres=(32, 32))
+        a = ops.fuse_argmax_confusion(views, codes, (224, 224), impl=0, **kw)
+        b = ops.fuse_argmax_confusion(views, codes, (224, 224), impl=IMPL_GENERIC, **kw)
+        assert torch.equal(a["labels"], b["labels"]), (family, r)
+        assert torch.equal(a["lowres"].view(torch.int32), b["lowres"].view(torch.int32)), (family, r)   # bit patterns (NaN-safe)
+    st = _lib.filter_stats(0)
+    assert st["multi_tiles"] > 0
+    print(f"[{family}] multi-label tiles {st['multi_tiles']}, exact-pass pixels {st['exact_pixels']} "
+          f"({st['exact_pixels'] / max(st['multi_tiles'] * 224 * 224, 1):.2e} of their pixels), whole-tile exact {st['exact_tiles']}")
+
+
+def test_bit_stability_over_1000_launches(cuda):
+    """Warp-specialised producer / mbarrier / TMA pipeline + shared-memory queue + dynamic tile scheduler: 1000 launches on the same
+    inputs must give identical bytes every time (a race would show up as a flipped label or a different 32x32 value sooner or later)."""
+    cfg = synthetic.cfg2(N=600)
+    views = [v.to(cuda) for v in cfg["views"]]
+    kw = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=cfg["present"].to(cuda), bg=cfg["bg"].to(cuda), bg_match=1, bg_label=3, lowres=(32, 32))
+    ref = ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), **kw)
+    lab0, low0 = ref["labels"].clone(), ref["lowres"].clone()
+    bad = torch.zeros((), dtype=torch.int64, device=cuda)
+    for i in range(1000):
+        out = ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), **kw)
+        bad += (out["labels"] != lab0).sum() + (out["lowres"].view(torch.int32) != low0.view(torch.int32)).sum()
+    assert int(bad.item()) == 0

@@ -65,9 +65,29 @@ def fuse_case(name, cfg, N, steps=20, **kw):
 fuse_case("cfg1 single stride-8 view, bg+gt+labels+confusion (C=3)", synthetic.cfg1(N=1024), 16384, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)
 fuse_case("cfg2 pseudo-mask: 3 scales x flip, present, bg, labels, 32x32 (C=3)", synthetic.cfg2(N=1024), 16384, mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
 fuse_case("cfg2 all multi-label tiles", synthetic.cfg2(N=1024, single_frac=0.0), 16384, mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
+# data dependence of the filtered kernel: the same cfg-2 call on other input families, with the fraction of
+# pixels that went through the exact pass and the number of tiles evaluated exactly as a whole (pisto_filter_stats)
+def family_case(family, N=16384):
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    sizes, codes = [21, 21, 28, 28, 35, 35], [0, 4, 0, 4, 0, 4]
+    views = synthetic.family_views(family, N, sizes, gen, dev)
+    base = synthetic.cfg2(N=1024)
+    present, bg = rep(base["present"], N), rep(base["bg"], N)
+    fn = lambda: ops.fuse_argmax_confusion(views, codes, (224, 224), mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, present=present, bg=bg, bg_match=1,
+                                           bg_label=3, lowres=(32, 32))
+    fn(); _lib.filter_stats(0, reset=True)
+    fn(); st = _lib.filter_stats(0, reset=True)
+    ms = timeit(fn, 20)
+    emit(f"cfg2 on '{family}' logits (40% single-label tiles)", N, "tiles", ms, 171440,
+         exact_pixel_frac=st["exact_pixels"] / max(st["multi_tiles"] * 224 * 224, 1), whole_tile_exact_frac=st["exact_tiles"] / max(st["multi_tiles"], 1),
+         multi_tiles=st["multi_tiles"])
+
+
+for fam in ("gauss", "smooth", "quantized", "neartie", "extreme"):
+    family_case(fam)
 fuse_case("cfg3 BCSS: 3 scales x flip, gt, labels, confusion (C=4)", synthetic.cfg3(N=1000), 10000, decide=DECIDE_SOFTMAX)
 fuse_case("cfg2 PROB_MEAN fusion (softmax per view)", synthetic.cfg2(N=1024), 8192, fuse_mode=FUSE_PROB_MEAN, decide=DECIDE_RAW, bg_match=1, bg_label=3)
-for T, N in ((512, 512), (1024, 128)):
+for T, N in ((512, 512), (1024, 128), (2048, 32)):
     fuse_case(f"cfg5 large tile T={T}: 5 scales x flip, gt, labels, confusion (C=4)", synthetic.cfg5(N=8, T=T), N, steps=5, decide=DECIDE_SOFTMAX)
 # reference-literal Mode F: 8 full-resolution d4 views
 from pistoseg_b200 import tta  # noqa: E402
