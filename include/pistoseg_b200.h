@@ -79,7 +79,8 @@ int64_t pisto_launch_count(pisto_handle_t h);
 /* Data-dependence record of the filtered fusion kernels (the label fast path trusts a pixel only above an error-bound margin and
  * re-evaluates the others exactly): out_host[1] = multi-label tiles processed, out_host[2] = pixels that went through the exact
  * pass, out_host[3] = tiles evaluated exactly as a whole (queue overflow, non-finite / absurd logits, empty presence vector);
- * out_host[0] is reserved.  Synchronises the device; reset != 0 zeroes the counters afterwards. */
+ * out_host[0] = mosaic cells still rejected by the "background < 80 %" test at the last of max_tries draws (pisto_mosaic_plan_cells
+ * accepts them -- the reference would loop for ever -- but never silently).  Synchronises the device; reset != 0 zeroes the counters afterwards. */
 int pisto_filter_stats(pisto_handle_t h, unsigned long long* out_host /* [4] */, int reset);
 
 /* -------------------------------------------------------------------------------------------------- */
@@ -256,6 +257,12 @@ int pisto_mosaic_bg_integral(pisto_handle_t h, const uint8_t* pool_bg, const int
 int pisto_mosaic_plan_cells(pisto_handle_t h, uint64_t seed, int64_t first_index, int64_t index_stride, int N, int patch_num,
                             int patch_size, int P, const int32_t* pool_hw, const uint16_t* integral, const int64_t* integral_off,
                             int bg_label, int max_tries, pisto_mosaic_cell_t* cells /* [N][4][patch_num^2] */, pisto_stream_t stream);
+/* The per-quadrant decisions of the same mosaics (create_dataset.ipynb:324-354: split, Flip, ShiftScaleRotate -> inverse affine in
+ * float64, RandomCrop origin), also a pure function of (seed, i): Philox draws, explicit round-to-nearest float64 arithmetic and a
+ * fixed cos / sin polynomial, bit-identical to pistoseg_b200/mosaic.py::MosaicPlanner.quad_plans on the host. */
+int pisto_mosaic_plan_quads(pisto_handle_t h, uint64_t seed, int64_t first_index, int64_t index_stride, int N, int patch_num, int patch_size,
+                            double p_flip, double p_warp, double shift_limit, double scale_limit, double rotate_limit,
+                            pisto_mosaic_plan_t* plans, pisto_stream_t stream);
 
 /* normalise + resize + sum over scales in one pass (segmentation_test.py:187-199, prepare_seg_inputs.py:128-134):
  *   out[c] (+)= bilinear_f64( canvas[c] / max(count, min_count if > 0) ) resized from (hi, wi) to (ho, wo);

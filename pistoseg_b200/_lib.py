@@ -70,6 +70,7 @@ SYMBOLS = {
     "pisto_destroy": (_i, [_vp]),
     "pisto_launch_count": (_i64, [_vp]),
     "pisto_filter_stats": (_i, [_vp, _vp, _i]),
+    "pisto_mosaic_plan_quads": (_i, [_vp, C.c_uint64, _i64, _i64, _i, _i, _i, _d, _d, _d, _d, _d, _vp, _vp]),
     "pisto_confusion_accumulate": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "pisto_fuse_argmax_confusion": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _vp]),
     "pisto_fuse_argmax_confusion_host": (_i, [_vp, C.POINTER(View), _i, C.POINTER(FuseArgs), _i]),
@@ -147,5 +148,5 @@ def filter_stats(device=0, reset=True):
     """dict(multi_tiles, exact_pixels, exact_tiles) of the filtered fusion kernels since the last reset (pisto_filter_stats)."""
     buf = (C.c_ulonglong * 4)()
     check(load().pisto_filter_stats(handle(device), buf, int(bool(reset))))
-    return {"multi_tiles": int(buf[1]), "exact_pixels": int(buf[2]), "exact_tiles": int(buf[3])}
+    return {"multi_tiles": int(buf[1]), "exact_pixels": int(buf[2]), "exact_tiles": int(buf[3]), "mosaic_cells_exhausted": int(buf[0])}
 

@@ -265,9 +265,13 @@ __device__ __forceinline__ void pisto_softmax_inplace(float (&x)[C]) {
 }
 
 // Same softmax for the streaming kernels' PROB_MEAN path, where V*C*T^2 exponentials per tile make the MUFU unit the
-// bottleneck: exp as ex2.approx(x * log2 e) (relative error < 4e-7 on the argument range of a max-subtracted softmax) and one
-// reciprocal instead of C divisions.  Probabilities differ from the exact version by < 1e-6 absolute -- inside the 1e-5
-// float gate that applies to PROB_MEAN scores anyway (CUDA expf and the reference's Sleef expf already differ by 1 ulp).
+// bottleneck: exp(d) as ONE ex2.approx.ftz of d * log2(e) (relative error < 2^-22 on the argument range of a max-subtracted
+// softmax; results below 2^-126 flush to zero, i.e. < 1e-38 absolute) and ONE rcp.approx.ftz instead of C divisions (the correctly
+// rounded __frcp_rn / __expf expand to ~10 instructions with branches each: they were 45 % of this kernel's instructions).
+// Probabilities differ from the exact version by < 1e-6 absolute -- inside the 1e-5 float gate that applies to PROB_MEAN scores
+// anyway (CUDA expf and the reference's Sleef expf already differ by 1 ulp).
+__device__ __forceinline__ float pisto_ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float pisto_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <int C>
 __device__ __forceinline__ void pisto_softmax_fast(float (&x)[C]) {
   float m = x[0];
@@ -276,10 +280,10 @@ __device__ __forceinline__ void pisto_softmax_fast(float (&x)[C]) {
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < C; c++) {
-    x[c] = __expf(__fsub_rn(x[c], m));
-    sum = __fadd_rn(sum, x[c]);
+    x[c] = pisto_ex2_approx(__fmul_rn(__fsub_rn(x[c], m), 1.4426950408889634f));
+    sum = c == 0 ? x[c] : __fadd_rn(sum, x[c]);
   }
-  const float r = __frcp_rn(sum);
+  const float r = pisto_rcp_approx(sum);   // sum is in [1, C]: no denormal / overflow case
 #pragma unroll
   for (int c = 0; c < C; c++) x[c] = __fmul_rn(x[c], r);
 }

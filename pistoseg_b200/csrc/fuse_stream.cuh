@@ -33,7 +33,10 @@
 
 namespace {
 
-constexpr int kMaxThreads = 384;
+#ifndef PISTO_STREAM_THREADS
+#define PISTO_STREAM_THREADS 384
+#endif
+constexpr int kMaxThreads = PISTO_STREAM_THREADS;
 
 struct StreamGeom {
   int GX, S, rows_per_strip, threads;  // threads = compute warps * 32 + one producer warp
@@ -616,7 +619,13 @@ template <int C, int V>
 static int pisto_launch_stream_cv(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
   for (int v = 0; v < p.V; v++)
     if (p.view[v].map.ho >= p.T_h) return PISTO_OK;  // same-size / down-sampling rows: the source-row pair does not move by exactly one -> block kernel
-  if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) return launch_cv<C, V, true, -1, false>(h, p, st, launched);
+  if (p.fuse_mode == PISTO_FUSE_PROB_MEAN) {
+    switch (pisto_stream_flags(p)) {
+      case 17: return launch_cv<C, V, true, 17, false>(h, p, st, launched);  // bg + labels
+      case 16: return launch_cv<C, V, true, 16, false>(h, p, st, launched);  // labels
+      default: return launch_cv<C, V, true, -1, false>(h, p, st, launched);
+    }
+  }
   if ((V % 2 == 0) && pisto_stream_pairs(p)) {
     switch (pisto_stream_flags(p)) {
       case 25: return launch_cv<C, V, false, 25, (V % 2 == 0)>(h, p, st, launched);

@@ -24,6 +24,11 @@ def save_mask_png(mask_u8, path, palette, size_wh=None):
     im.save(path)
 
 
+def save_rgb_png(img_u8, path):
+    """RGB PNG of a mosaic image (create_dataset.ipynb:546)."""
+    Image.fromarray(np.ascontiguousarray(img_u8, dtype=np.uint8), mode="RGB").save(path)
+
+
 class AsyncWriter:
     def __init__(self, workers=8):
         self.pool = ThreadPoolExecutor(max_workers=workers)

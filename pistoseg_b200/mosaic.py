@@ -22,10 +22,37 @@ CELL_DTYPE = np.dtype([("tile", "<i4"), ("cy", "<i2"), ("cx", "<i2")])
 assert PLAN_DTYPE.itemsize == C.sizeof(_lib.MosaicPlan) and CELL_DTYPE.itemsize == C.sizeof(_lib.MosaicCell)
 
 
+_COS_COEF = [1.0 / 20922789888000.0, -1.0 / 87178291200.0, 1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5, 1.0]
+_SIN_COEF = [1.0 / 355687428096000.0, -1.0 / 1307674368000.0, 1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0,
+             -1.0 / 6.0, 1.0]
+
+
+def cos_sin_deg(angle):
+    """cos and sin of an angle in DEGREES, the same fixed arithmetic as ``pisto_cos_sin_deg`` in csrc/mosaic_plan.cu (quadrant
+    reduction in degrees, Taylor polynomials in Horner form with separate multiply and add): the device planner and this host
+    planner agree bit for bit, which the platforms' libm cos / sin would not guarantee.  |error| < 5e-16 against libm."""
+    angle = np.asarray(angle, np.float64)
+    k = np.rint(angle / 90.0)
+    r = angle + -(90.0 * k)
+    a = r * (3.14159265358979323846 / 180.0)
+    z = a * a
+    pc = np.full_like(a, _COS_COEF[0])
+    for c in _COS_COEF[1:]:
+        pc = pc * z + c
+    ps = np.full_like(a, _SIN_COEF[0])
+    for c in _SIN_COEF[1:]:
+        ps = ps * z + c
+    ps = ps * a
+    q = k.astype(np.int64) & 3
+    co = np.where(q == 0, pc, np.where(q == 1, -ps, np.where(q == 2, -pc, ps)))
+    si = np.where(q == 0, ps, np.where(q == 1, pc, np.where(q == 2, -ps, -pc)))
+    return co, si
+
+
 def rotation_matrix(center, angle, scale):
-    """cv2.getRotationMatrix2D in float64 (same operation order)."""
-    a = angle * (np.pi / 180.0)
-    alpha, beta = np.cos(a) * scale, np.sin(a) * scale
+    """cv2.getRotationMatrix2D in float64 (same operation order; cos / sin from ``cos_sin_deg``)."""
+    co, si = cos_sin_deg(angle)
+    alpha, beta = float(co) * scale, float(si) * scale
     cx, cy = center
     return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy], [-beta, alpha, beta * cx + (1 - alpha) * cy]], np.float64)
 
@@ -133,8 +160,8 @@ class MosaicPlanner:
     Per-cell decisions (source tile, crop origin, background rejection: 4 * patch_num^2 per mosaic) come from
     ``pisto_mosaic_plan_cells`` on the device (``cells_device``) or from the identical numpy arithmetic (``cells_host``);
     the per-quadrant decisions (split, flip, ShiftScaleRotate parameters -> inverse affine in float64, RandomCrop origin:
-    16 numbers per mosaic) are evaluated on the host, vectorised over mosaics, because their float64 trigonometry must be
-    the host's for the affine maps to equal cv2's bit for bit.
+    16 numbers per mosaic) likewise: ``quads_device`` (``pisto_mosaic_plan_quads``) or ``quad_plans`` (numpy) -- the same Philox
+    draws, the same float64 operation order and the same fixed cos / sin polynomial (``cos_sin_deg``), bit for bit.
     """
 
     def __init__(self, pool, patch_num, patch_size, seed=2022, reject_bg=False, bg_label=3,
@@ -191,6 +218,17 @@ class MosaicPlanner:
                                                int(self.bg_label), int(self.max_tries), ops._ptr(cells), ops._stream(dev)))
         return cells
 
+    def quads_device(self, first_index, index_stride, N):
+        """CUDA uint8 view of MosaicPlan[N] for mosaics first_index + k * index_stride (pisto_mosaic_plan_quads)."""
+        device = self.pool.dev["img"].device
+        dev = device.index if device.index is not None else torch.cuda.current_device()
+        plans = torch.empty(N * PLAN_DTYPE.itemsize, dtype=torch.uint8, device=device)
+        lib = _lib.load()
+        _lib.check(lib.pisto_mosaic_plan_quads(_lib.handle(dev), self.seed & 0xFFFFFFFFFFFFFFFF, int(first_index), int(index_stride), int(N), self.pn, self.ps,
+                                               float(self.p_flip), float(self.p_warp), float(self.shift_limit), float(self.scale_limit),
+                                               float(self.rotate_limit), ops._ptr(plans), ops._stream(dev)))
+        return plans
+
     # ---- per-quadrant decisions -----------------------------------------------------------------------------------
     def quad_plans(self, indices):
         """[N] PLAN_DTYPE: split, and per quadrant flip code, warp flag + inverse affine, crop origin."""
@@ -239,10 +277,10 @@ class MosaicPlanner:
 
 def shift_scale_rotate_batch(H, W, angle, scale, dx, dy):
     """``shift_scale_rotate_matrix`` over arrays, same float64 operation order -> [N, 2, 3]."""
-    a = angle * (np.pi / 180.0)
-    alpha, beta = np.cos(a) * scale, np.sin(a) * scale
+    co, si = cos_sin_deg(angle)
+    alpha, beta = co * scale, si * scale
     cx, cy = W / 2 - 0.5, H / 2 - 0.5
-    M = np.empty((len(a), 2, 3), np.float64)
+    M = np.empty((len(alpha), 2, 3), np.float64)
     M[:, 0, 0] = alpha; M[:, 0, 1] = beta; M[:, 0, 2] = (1 - alpha) * cx - beta * cy
     M[:, 1, 0] = -beta; M[:, 1, 1] = alpha; M[:, 1, 2] = beta * cx + (1 - alpha) * cy
     M[:, 0, 2] += dx * W
@@ -268,15 +306,46 @@ def synthesize(pool, plans, cells, patch_num, patch_size, bg_label=3, packed=Tru
     """plans [N] PLAN_DTYPE (numpy), cells [N,4,pn*pn] CELL_DTYPE (numpy) or the CUDA uint8 tensor of ``cells_device``
     -> (img u8 [N,S,S,3], mask u8 [N,S,S]) CUDA tensors."""
     device = pool.dev["img"].device
-    p = torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(-1)).to(device)
+    p = plans if torch.is_tensor(plans) else torch.from_numpy(np.ascontiguousarray(plans).view(np.uint8).reshape(-1)).to(device)
     c = cells if torch.is_tensor(cells) else torch.from_numpy(np.ascontiguousarray(cells).view(np.uint8).reshape(-1)).to(device)
     return ops.mosaic_gather(pool.dev, p, c, patch_num, patch_size, bg_label, packed=packed)
 
 
-def synthesize_range(pool, planner, first_index, index_stride, N, bg_label=3):
-    """Mosaics first_index + k * index_stride, k < N: quadrant plans on the host (vectorised), cells on the device."""
-    idx = [first_index + k * index_stride for k in range(N)]
-    return synthesize(pool, planner.quad_plans(idx), planner.cells_device(first_index, index_stride, N), planner.pn, planner.ps, bg_label)
+def synthesize_range(pool, planner, first_index, index_stride, N, bg_label=3, host_quads=False):
+    """Mosaics first_index + k * index_stride, k < N: quadrant plans and cells both planned on the device (host_quads=True: the
+    quadrant plans from the numpy planner instead -- identical bits)."""
+    if host_quads:
+        quads = planner.quad_plans([first_index + k * index_stride for k in range(N)])
+    else:
+        quads = planner.quads_device(first_index, index_stride, N)
+    return synthesize(pool, quads, planner.cells_device(first_index, index_stride, N), planner.pn, planner.ps, bg_label)
+
+
+def export_dataset(pool, planner, out_dir, n_total, rank=0, world=1, chunk=4096, dataset="wsss4luad", writer=None, name_fmt="{:07d}.png"):
+    """The export driver of create_dataset.ipynb:523-560 (``func(indexes)``): rank r of ``world`` synthesises the mosaics
+    ``i = r (mod world)`` and writes ``<out_dir>/img/<i>.png`` (RGB) and ``<out_dir>/mask/<i>.png`` (mode 'P' with the dataset's
+    palette), chunk by chunk: the GPU gathers chunk k + 1 while the host threads encode chunk k.  Returns the number written."""
+    import os
+    from . import io as pio
+    os.makedirs(os.path.join(out_dir, "img"), exist_ok=True)
+    os.makedirs(os.path.join(out_dir, "mask"), exist_ok=True)
+    palette = pio.palette_for(dataset)
+    own = writer is None
+    writer = writer or pio.AsyncWriter()
+    mine = len(range(rank, n_total, world))
+    done = 0
+    for k0 in range(0, mine, chunk):
+        n = min(chunk, mine - k0)
+        img, mask = synthesize_range(pool, planner, rank + k0 * world, world, n)
+        img_h, mask_h = img.cpu().numpy(), mask.cpu().numpy()
+        for k in range(n):
+            i = rank + (k0 + k) * world
+            writer.submit(pio.save_rgb_png, img_h[k], os.path.join(out_dir, "img", name_fmt.format(i)))
+            writer.submit(pio.save_mask_png, mask_h[k], os.path.join(out_dir, "mask", name_fmt.format(i)), palette)
+        done += n
+    if own:
+        writer.close()
+    return done
 
 
 def shard_indices(n_total, rank, world):

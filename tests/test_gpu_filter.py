@@ -187,6 +187,25 @@ def test_band_kernel_large_tiles(cuda, T, C, scales):
     assert torch.equal(c["labels"], b["labels"])
 
 
+def test_large_tile_2048_against_the_oracle(cuda):
+    """BASELINE config 5 at its largest size (T = 2048, C = 4, 5 scales x flip: V = 10, views of 256..512 px), one tile: the block-tiled
+    filtered kernel (automatic dispatch) == the generic kernel bit for bit, and both against the CPU oracle (torch bilinear + sum in
+    view order): labels >= 99.99 %, confusion matrix equal up to those pixels."""
+    T, C = 2048, 4
+    cfg = synthetic.cfg5(N=1, T=T, C=C)
+    out = run(cfg, cuda, 0, decide=DECIDE_SOFTMAX)
+    ref = run(cfg, cuda, IMPL_GENERIC, decide=DECIDE_SOFTMAX)
+    assert torch.equal(out["labels"], ref["labels"]) and torch.equal(out["conf"], ref["conf"])
+    fused = ofuse.fuse_views(cfg["views"], cfg["codes"], (T, T))
+    pred = ofuse.miou_pred(fused).numpy()
+    lab = out["labels"].cpu().numpy()
+    agree = float((lab == pred).mean())
+    assert agree >= 0.9999, agree
+    cm = oconf.generate_matrix(pred[0], cfg["gt"][0].numpy(), C)
+    assert np.abs(out["conf"].cpu().numpy() - cm).sum() <= 2 * (lab != pred).sum()
+    assert int(out["conf"].sum()) == int((cfg["gt"] < C).sum())
+
+
 def test_full_size_runs_through_size_independent_properties(cuda):
     """BASELINE sizes (16 384 cfg-2 tiles in one launch, 10 000 cfg-3 tiles): the batch is a seeded block repeated, so
     (i) every repetition must reproduce the block's labels / 32x32 logits bit for bit whichever CTA processed it and in

@@ -141,3 +141,59 @@ def test_device_planner_equals_host_planner(cuda, pn, ps, with_bg):
     # 64-bit mosaic indices
     big = planner.cells_device(2 ** 33 + 1, 1, 2).cpu().numpy().view(mosaic.CELL_DTYPE).reshape(2, 4, pn * pn)
     assert np.array_equal(big, planner.cells_host([2 ** 33 + 1, 2 ** 33 + 2]))
+
+
+@pytest.mark.parametrize("pn,ps", [(4, 56), (7, 32)])
+def test_device_quadrant_planner_equals_host_planner(cuda, pn, ps):
+    """pisto_mosaic_plan_quads == MosaicPlanner.quad_plans byte for byte (split, flip, warp flag, float64 inverse affine, crop
+    origin) over 4 096 strided indices and beyond 2^32."""
+    rng = np.random.default_rng(3)
+    imgs, bgs, labels = make_pool(rng, 12, ps, False)
+    pool = mosaic.TilePool(imgs, labels, bgs, device=cuda)
+    planner = mosaic.MosaicPlanner(pool, pn, ps, seed=2022)
+    for first, stride, N in [(0, 1, 4096), (3, 8, 1000), (2 ** 33 + 5, 7, 64)]:
+        host = planner.quad_plans([first + k * stride for k in range(N)])
+        dev = planner.quads_device(first, stride, N).cpu().numpy().view(mosaic.PLAN_DTYPE)
+        assert host.tobytes() == dev.tobytes(), (first, stride)
+    assert planner.quads_device(0, 1, 0).numel() == 0
+
+
+def test_rejection_loop_exhaustion_is_counted(cuda):
+    """The reference's `while True` rejection loop (create_dataset.ipynb:303-309) never ends on a pool that is all background; the
+    device planner accepts the draw number max_tries and counts the cell (pisto_filter_stats slot 0) instead of hiding it."""
+    from pistoseg_b200 import _lib
+    rng = np.random.default_rng(4)
+    pn, ps, P = 4, 56, 6
+    imgs = [rng.integers(0, 256, (224, 224, 3), dtype=np.uint8) for _ in range(P)]
+    bgs = [np.full((224, 224), 255, np.uint8) for _ in range(P)]
+    pool = mosaic.TilePool(imgs, rng.integers(0, 3, P).astype(np.uint8), bgs, device=cuda)
+    planner = mosaic.MosaicPlanner(pool, pn, ps, seed=1, reject_bg=True, max_tries=3)
+    _lib.filter_stats(cuda.index or 0, reset=True)
+    N = 8
+    planner.cells_device(0, 1, N)
+    assert _lib.filter_stats(cuda.index or 0, reset=True)["mosaic_cells_exhausted"] == N * 4 * pn * pn
+    bgs = [np.zeros((224, 224), np.uint8) for _ in range(P)]
+    pool = mosaic.TilePool(imgs, rng.integers(0, 3, P).astype(np.uint8), bgs, device=cuda)
+    mosaic.MosaicPlanner(pool, pn, ps, seed=1, reject_bg=True, max_tries=3).cells_device(0, 1, N)
+    assert _lib.filter_stats(cuda.index or 0, reset=True)["mosaic_cells_exhausted"] == 0
+
+
+def test_export_dataset_writes_the_notebook_layout(cuda, tmp_path):
+    """create_dataset.ipynb:523-560: rank r writes img/<i>.png (RGB) and mask/<i>.png (mode P, dataset palette) for i = r (mod G);
+    the union over ranks is every index once and the decoded pixels are the synthesised ones."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    pn, ps = 4, 16
+    imgs, bgs, labels = make_pool(rng, 12, ps, True)
+    pool = mosaic.TilePool(imgs, labels, bgs, device=cuda)
+    planner = mosaic.MosaicPlanner(pool, pn, ps, seed=9, reject_bg=True)
+    n_total, world = 21, 2
+    wrote = [mosaic.export_dataset(pool, planner, str(tmp_path), n_total, rank=r, world=world, chunk=4) for r in range(world)]
+    assert wrote == [11, 10]
+    names = sorted(os.listdir(tmp_path / "img"))
+    assert names == sorted(os.listdir(tmp_path / "mask")) == [f"{i:07d}.png" for i in range(n_total)]
+    img, msk = mosaic.synthesize_range(pool, planner, 0, 1, n_total)
+    for i in (0, 1, 10, 20):
+        im = Image.open(tmp_path / "img" / f"{i:07d}.png"); mk = Image.open(tmp_path / "mask" / f"{i:07d}.png")
+        assert im.mode == "RGB" and mk.mode == "P"
+        assert np.array_equal(np.asarray(im), img[i].cpu().numpy()) and np.array_equal(np.asarray(mk), msk[i].cpu().numpy())

@@ -168,10 +168,11 @@ for pn, ps in ((4, 56), (2, 112), (7, 32)):
     pl = torch.from_numpy(plans.view(np.uint8).reshape(-1)).to(dev)
     ms = timeit(lambda: ops.mosaic_gather(pool.dev, pl, cells, pn, ps, 3), 5)
     emit(f"mosaic_gather {pn}x{ps} (224x224 image+mask, 80% warped quadrants)", N, "mosaics", ms, 2 * (224 * 224 * 4),
-         plan_cells_device_us_per_mosaic=ms_cells / N * 1e3, plan_quads_host_us_per_mosaic=quad_s / N * 1e6)
+         plan_cells_device_us_per_mosaic=ms_cells / N * 1e3, plan_quads_host_us_per_mosaic=quad_s / N * 1e6,
+         plan_quads_device_us_per_mosaic=timeit(lambda: planner.quads_device(0, 1, N), 5) / N * 1e3)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for r in range(3):
         mosaic.synthesize_range(pool, planner, r * N, 1, N)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
-    emit(f"mosaic end to end {pn}x{ps}: host quadrant plans + device cell plans + gather (wall clock)", N, "mosaics", dt * 1e3, 2 * (224 * 224 * 4))
+    emit(f"mosaic end to end {pn}x{ps}: device quadrant plans + device cell plans + gather (wall clock)", N, "mosaics", dt * 1e3, 2 * (224 * 224 * 4))
 fout.close()

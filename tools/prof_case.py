@@ -4,13 +4,14 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from pistoseg_b200 import ops, synthetic
-from pistoseg_b200._lib import DECIDE_SOFTMAX, MASK_FILL
+from pistoseg_b200._lib import DECIDE_RAW, DECIDE_SOFTMAX, FUSE_PROB_MEAN, MASK_FILL
 dev = torch.device("cuda:0")
 name, impl = sys.argv[1], int(sys.argv[2])
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 kw2 = dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))
 cfg, kw = {"cfg2": (lambda: synthetic.cfg2(N=1024), kw2), "cfg2multi": (lambda: synthetic.cfg2(N=1024, single_frac=0.0), kw2),
            "cfg2multinolow": (lambda: synthetic.cfg2(N=1024, single_frac=0.0), dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)),
+           "cfg2prob": (lambda: synthetic.cfg2(N=1024), dict(fuse_mode=FUSE_PROB_MEAN, decide=DECIDE_RAW, bg_match=1, bg_label=3)),
            "cfg2single": (lambda: synthetic.cfg2(N=1024, single_frac=1.0), kw2),
            "cfg1": (lambda: synthetic.cfg1(N=1024), dict(decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3)),
            "cfg3": (lambda: synthetic.cfg3(N=1000), dict(decide=DECIDE_SOFTMAX)),
