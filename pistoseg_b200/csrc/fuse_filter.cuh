@@ -86,6 +86,10 @@ struct FCtl {
   unsigned int qcount[2];   // uncertain pixels queued by the row loop
   unsigned int lownext[2];  // next low-resolution row of the logit export to be claimed (any warp may claim)
   unsigned int hist[64];
+  // fuse_static.cuh: everything a consumer thread needs to know about the published tile in one 16-byte load, prepared by the
+  // producer lane: {presence bits, single label or -1, candidate classes (one byte each, ascending), staging shifts of the
+  // views ((address & 12) >> 2, two bits per view) | number of candidates << 28}
+  uint4 head[2];
 };
 
 // label among cls[0..K] from the difference candidates (0, d[0] .. d[K-1]); returns whether the lead exceeds tau

@@ -424,8 +424,18 @@ __device__ __forceinline__ void static_push_rows(FCtl* ctl, uint32_t* queue, int
 
 // ---- pre-pass: Y[g][k] = sum over the views of group g of (x[c_{k+1}] - x[c_0]) in the de-augmented frame, maps padded by one
 // replicated row above / below and two replicated columns on the right; returns the thread's max |x| (NaN-propagating)
+// tidr[g]: the thread's index rotated by the number of cells of the groups before g (mod nt), so that the partial last sweeps of the
+// groups land on different threads and every thread handles ceil or floor of (cells / nt) cells in total (static_prepass_rot)
+__host__ __device__ constexpr int st_rot_off(int G, int g, int nt) { int off = 0; for (int q = 0; q < g; q++) off = (off + st_h(G, q) * st_h(G, q)) % nt; return off; }
+template <int G, int NT>
+__device__ __forceinline__ void static_prepass_rot(int tid, int (&tidr)[G]) {
+  static_for<0, G>([&](auto GI) {
+    constexpr int gi = decltype(GI)::value, off = st_rot_off(G, gi, NT);
+    tidr[gi] = tid - off + (tid < off ? NT : 0);
+  });
+}
 template <int C, int G, int VPG, int K>
-__device__ __forceinline__ float static_prepass(const StaticGeom& g, const uint32_t (&vb)[G * VPG], const int (&cls)[C], uint32_t ymap_s, int tid, int nt) {
+__device__ __forceinline__ float static_prepass(const StaticGeom& g, const uint32_t (&vb)[G * VPG], const int (&cls)[C], uint32_t ymap_s, const int (&tidr)[G], int nt) {
   constexpr int KP = K == 3 ? 4 : K;
   constexpr uint32_t ES = 4u * KP;
   float mxf = 0.f;
@@ -439,7 +449,7 @@ __device__ __forceinline__ float static_prepass(const StaticGeom& g, const uint3
 #pragma unroll
     for (int q = 0; q < K; q++) dq[q] = (cls[q + 1] - cls[0]) * PL;
 #pragma unroll 2
-    for (int idx = tid; idx < h * h; idx += nt) {
+    for (int idx = tidr[gi]; idx < h * h; idx += nt) {
       const int i = idx / h, j = idx - i * h;
       const uint32_t aa = basea + 4 * h * i + j * ca, ab = baseb + 4 * h * i + j * cb;
       const float x0a = lds_f32(aa), x0b = VPG == 2 ? lds_f32(ab) : 0.f;
@@ -498,26 +508,105 @@ __device__ __forceinline__ void static_export_unit(float* out_n, int c, const ui
   static_for<0, G>([&](auto GI) {
     constexpr int gi = decltype(GI)::value, h = st_h(G, gi), PL = 4 * h * h, RB = 4 * h;
     constexpr int imin = lo_i0(h, RPU * E), imax = lo_i1(h, RPU * E + RPU - 1);
-#pragma unroll 1
-    for (int tw = 0; tw < VPG; tw++) {
-      const uint32_t b0 = (tw ? sA[gi * VPG + VPG - 1] : sA[gi * VPG]) + (uint32_t)(c * PL);
-      const uint32_t b1 = (tw ? sB[gi * VPG + VPG - 1] : sB[gi * VPG]) + (uint32_t)(c * PL);
-      float Hr[imax - imin + 1];
+    if constexpr (VPG == 2) {
+      // a scale and its flipped twin: the two samples ride in the two lanes of the packed f32x2 operations (each lane is the
+      // same IEEE operation as the scalar code), the two adds of the view-order sum stay scalar and sequential
+      const uint32_t b0 = sA[2 * gi] + (uint32_t)(c * PL), b1 = sB[2 * gi] + (uint32_t)(c * PL);
+      const uint32_t t0 = sA[2 * gi + 1] + (uint32_t)(c * PL), t1 = sB[2 * gi + 1] + (uint32_t)(c * PL);
+      const u64 LX0 = pack2(lx0[gi], lx0[gi]), LX1 = pack2(lx1[gi], lx1[gi]);
+      u64 Hr[imax - imin + 1];
       static_for<imin, imax + 1>([&](auto II) {
         constexpr int i = decltype(II)::value;
-        Hr[i - imin] = __fmaf_rn(lx0[gi], lds_f32_o<i * RB>(b0), __fmul_rn(lx1[gi], lds_f32_o<i * RB>(b1)));
+        Hr[i - imin] = fma2(LX0, pack2(lds_f32_o<i * RB>(b0), lds_f32_o<i * RB>(t0)), mul2(LX1, pack2(lds_f32_o<i * RB>(b1), lds_f32_o<i * RB>(t1))));
       });
       static_for<0, RPU>([&](auto RI) {
         constexpr int r = decltype(RI)::value, ly = RPU * E + r;
         constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
-        const float u = __fmaf_rn(l0, Hr[lo_i0(h, ly) - imin], __fmul_rn(l1, Hr[lo_i1(h, ly) - imin]));
-        a[r] = __fadd_rn(a[r], u);
+        float ua, ub;
+        unpack2(fma2(pack2(l0, l0), Hr[lo_i0(h, ly) - imin], mul2(pack2(l1, l1), Hr[lo_i1(h, ly) - imin])), ua, ub);
+        a[r] = __fadd_rn(__fadd_rn(a[r], ua), ub);
       });
+    } else {
+#pragma unroll 1
+      for (int tw = 0; tw < VPG; tw++) {
+        const uint32_t b0 = (tw ? sA[gi * VPG + VPG - 1] : sA[gi * VPG]) + (uint32_t)(c * PL);
+        const uint32_t b1 = (tw ? sB[gi * VPG + VPG - 1] : sB[gi * VPG]) + (uint32_t)(c * PL);
+        float Hr[imax - imin + 1];
+        static_for<imin, imax + 1>([&](auto II) {
+          constexpr int i = decltype(II)::value;
+          Hr[i - imin] = __fmaf_rn(lx0[gi], lds_f32_o<i * RB>(b0), __fmul_rn(lx1[gi], lds_f32_o<i * RB>(b1)));
+        });
+        static_for<0, RPU>([&](auto RI) {
+          constexpr int r = decltype(RI)::value, ly = RPU * E + r;
+          constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
+          const float u = __fmaf_rn(l0, Hr[lo_i0(h, ly) - imin], __fmul_rn(l1, Hr[lo_i1(h, ly) - imin]));
+          a[r] = __fadd_rn(a[r], u);
+        });
+      }
     }
   });
   float* outp = out_n + (c * kSLow + RPU * E) * kSLow + (threadIdx.x & 31);
+  // a / V: the arithmetic of static_div_views, two rows per packed operation; one range test for the whole unit
+  float lo = fabsf(a[0]), hi = lo;
 #pragma unroll
-  for (int r = 0; r < RPU; r++) outp[r * kSLow] = static_div_views(a[r], rcp_v, fV);
+  for (int r = 1; r < RPU; r++) { lo = fminf(lo, fabsf(a[r])); hi = fmaxf(hi, fabsf(a[r])); }
+  if (RPU % 2 == 0 && lo > 1e-30f && hi < 1e30f) {
+    const u64 R2 = pack2(rcp_v, rcp_v), NV2 = pack2(-fV, -fV);
+#pragma unroll
+    for (int r = 0; r < RPU; r += 2) {
+      const u64 a2 = pack2(a[r], a[r + 1 < RPU ? r + 1 : r]);
+      const u64 q2 = mul2(a2, R2);
+      float o0, o1;
+      unpack2(fma2(fma2(NV2, q2, a2), R2, q2), o0, o1);
+      outp[r * kSLow] = o0;
+      outp[(r + 1) * kSLow] = o1;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < RPU; r++) outp[r * kSLow] = static_div_slow(a[r], fV);  // (static: a[] must stay in registers)
+  }
+}
+
+// background overwrite of 4 x 16 labels (infer_pseudo_masks.py:86-88: label[bg == match] = bg_label).  Byte masks that hold only
+// 0 / 1 with match == 1 (what the reference's tissue masks are) take a multiply instead of the SWAR byte compare.
+__device__ __forceinline__ void static_bg_overwrite4(uint4 (&lv)[4], const uint4 (&bgv)[4], unsigned int m4, unsigned int bgl4) {
+  unsigned int any = 0;
+#pragma unroll
+  for (int u = 0; u < 4; u++) any |= bgv[u].x | bgv[u].y | bgv[u].z | bgv[u].w;
+  if (m4 == 0x01010101u && (any & 0xfefefefeu) == 0u) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      unsigned int eq;
+      eq = bgv[u].x * 0xffu; lv[u].x = (bgl4 & eq) | (lv[u].x & ~eq);
+      eq = bgv[u].y * 0xffu; lv[u].y = (bgl4 & eq) | (lv[u].y & ~eq);
+      eq = bgv[u].z * 0xffu; lv[u].z = (bgl4 & eq) | (lv[u].z & ~eq);
+      eq = bgv[u].w * 0xffu; lv[u].w = (bgl4 & eq) | (lv[u].w & ~eq);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      unsigned int eq;
+      eq = __vcmpeq4(bgv[u].x, m4); lv[u].x = (bgl4 & eq) | (lv[u].x & ~eq);
+      eq = __vcmpeq4(bgv[u].y, m4); lv[u].y = (bgl4 & eq) | (lv[u].y & ~eq);
+      eq = __vcmpeq4(bgv[u].z, m4); lv[u].z = (bgl4 & eq) | (lv[u].z & ~eq);
+      eq = __vcmpeq4(bgv[u].w, m4); lv[u].w = (bgl4 & eq) | (lv[u].w & ~eq);
+    }
+  }
+}
+
+// the per-tile head word of FCtl::head (producer lane)
+template <int C, int V>
+__device__ __forceinline__ uint4 static_tile_head(const FuseParams& p, int n, const TilePresence& tp) {
+  unsigned int clsw = 0, P = 0, vshw = 0;
+#pragma unroll
+  for (int c = 0; c < C; c++)
+    if ((tp.bits >> c) & 1u) { clsw |= (unsigned)c << (8 * P); P++; }
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    const ViewDev& vw = p.view[v];
+    vshw |= (((unsigned)reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) >> 2) & 3u) << (2 * v);
+  }
+  return make_uint4(tp.bits, (unsigned)tp.single, clsw, vshw | (P << 28));
 }
 
 template <int C, int G, int VPG, int F, int NB, int NP>
@@ -622,6 +711,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         ctl->pres_bits[b] = next_tp.bits;
         ctl->pres_single[b] = next_tp.single;
         ctl->lownext[b] = 0u;
+        if (tile >= 0) ctl->head[b] = static_tile_head<C, V>(p, tile, next_tp);
         if (tile >= 0 && next_views) issue_tile(tile, b);
         else mbar_arrive(&ctl->full[b]);
         if (tile < 0) break;
@@ -645,16 +735,25 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
 #pragma unroll
     for (int q = 0; q < G; q++) { const float2 t = lowwt[lane * G + q]; lx0[q] = t.x; lx1[q] = t.y; }
     float* out_n = p.lowres_out + (long long)n * C * kSLow * kSLow;
+    // units are claimed from a shared counter (export warps start early, compute warps join when their tile work is done)
+#ifdef PISTO_EXPORT_STATIC_UNITS  // warp w takes unit w: no gain measured over the shared counter (profiles/r02): off
+    const bool claim = g.aux != 0;
+#else
+    const bool claim = true;
+#endif
+    int u = claim ? 0 : (tid >> 5);
     for (;;) {
-      int u = 0;
-      if (lane == 0) u = (int)atomicAdd(&ctl->lownext[b], 1u);
-      u = __shfl_sync(0xffffffffu, u, 0);
+      if (claim) {
+        if (lane == 0) u = (int)atomicAdd(&ctl->lownext[b], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+      }
       if (u >= UNITS) break;
       const int c = u / kSNE, e = u - c * kSNE;
       static_for<0, kSNE>([&](auto EI) {
         constexpr int E = decltype(EI)::value;
         if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(out_n, c, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
       });
+      u += g.cwarps;
     }
   };
 
@@ -670,6 +769,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
   const uint32_t lab_s = smem_u32(labsm);
   const int nt = ncomp;
   constexpr long long tpx = (long long)kST * kST;
+  constexpr int NT = 32 * ((GX * kSS + 31) / 32);  // compute threads (= ncomp)
 
   for (int k = 0;; k++) {
     const int b = k & 1;
@@ -677,31 +777,21 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     mbar_wait(&ctl->full[sb], NB == 2 ? ((k >> 1) & 1) : (k & 1));
     const int n = ctl->tile[sb];
     if (n < 0) break;
+    const int4 hd = lds_i4(smem_u32(&ctl->head[sb]));
     uint32_t vb[V];
 #pragma unroll
-    for (int v = 0; v < V; v++) {
-      const ViewDev& vw = p.view[v];
-      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(vw.logits + (long long)n * vw.tile_stride) & 12u);
-      vb[v] = smem_u32(vsm + sb * g.buf_floats + g.view_off[v]) + sh;
-    }
+    for (int v = 0; v < V; v++) vb[v] = smem_u32(vsm) + 4u * (uint32_t)(sb * g.buf_floats + g.view_off[v]) + ((((unsigned)hd.w >> (2 * v)) & 3u) << 2);
     // (Measured and dropped: mbarrier-based phase barriers at which a waiting warp works off export units.  The arrive / try_wait
     // barrier itself cost 8 % against bar.sync and the filled waits returned less than that.)
     auto phase_sync = [&](int) { bar_sync(1, ncomp); };
     if (!is_export) {
-    TilePresence tp = pisto_tile_presence(p, n);
-    if (p.present) { tp.bits = ctl->pres_bits[sb]; tp.single = ctl->pres_single[sb]; }
+    TilePresence tp;
+    tp.bits = (unsigned)hd.x; tp.single = hd.y;
     const bool multi = tp.single < 0;
-    int cls[C], P = 0;
+    int cls[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) cls[c] = 0;
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      if ((tp.bits >> c) & 1u) {
-#pragma unroll
-        for (int q = 0; q < C; q++)
-          if (q == P) cls[q] = c;
-        P++;
-      }
+    for (int c = 0; c < C; c++) cls[c] = (int)(((unsigned)hd.z >> (8 * c)) & 0xffu);
+    const int P = (int)((unsigned)hd.w >> 28);
 
 #ifdef PISTO_X_SKIP_PREPASS
     if (false) {
@@ -709,15 +799,43 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     if (multi && P >= 2) {
 #endif
       float mxf;
-      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tid, nt);
-      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tid, nt);
-      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      int tidr[G];
+#ifdef PISTO_PREPASS_ROT  // balanced sweeps measured 2-4 % slower on B200 (profiles/r02): off
+      static_prepass_rot<G, NT>(tid, tidr);
+#else
+#pragma unroll
+      for (int q = 0; q < G; q++) tidr[q] = tid;
+#endif
+      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tidr, nt);
+      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tidr, nt);
+      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tidr, nt);
       const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
     phase_sync(0);  // difference maps + max visible; every thread has left the previous tile
     if (NB == 1 && (tid & 31) == 0) mbar_arrive(&ctl->empty[0]);
     if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone
+
+    // The byte masks of the vector pass' first batch are requested as soon as the registers are free -- right away for single-label
+    // tiles, after the row loop otherwise -- so that their latency is covered by the barrier and the exact pass.
+    constexpr int UN = 4;
+    const long long vbase_px = (long long)n * tpx;
+    const bool vec_ok = ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
+    const int nvec = vec_ok ? (int)(tpx / 16) : 0;
+    uint4 bgn[UN], gn[UN];
+    auto request_masks = [&]() {
+#pragma unroll
+      for (int u = 0; u < UN; u++) {
+        const int i = tid + u * nt;
+        gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        bgn[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nvec) {
+          if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + vbase_px) + i);
+          if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + vbase_px) + i);
+        }
+      }
+    };
+    if (!multi) request_masks();
 
     bool exact_all = false;
     if (multi) {
@@ -791,6 +909,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         else if (P == 3) static_push_rows<G, 2, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
         else static_push_rows<G, (C >= 4 ? 3 : 1), NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
       }
+      request_masks();
       phase_sync(1);  // every strip done: the queue is complete; everyone has read maxbits
       if (tid == 0) ctl->maxbits[b] = 0u;
       // Pixels that failed the lead test (about 1e-4 of them on Gaussian logits) are re-evaluated exactly -- operation by
@@ -843,22 +962,6 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
       }
     }
 
-    constexpr int UN = 4;
-    const long long vbase_px = (long long)n * tpx;
-    const bool vec_ok = ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
-    const int nvec = vec_ok ? (int)(tpx / 16) : 0;
-    uint4 bgn[UN], gn[UN];
-#pragma unroll
-    for (int u = 0; u < UN; u++) {
-      const int i = tid + u * nt;
-      gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      bgn[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (i < nvec) {
-        if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + vbase_px) + i);
-        if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + vbase_px) + i);
-      }
-    }
-
     // ---- vector pass: confusion, background overwrite, 16-byte label stores (single-label tiles: constant label)
 #ifdef PISTO_X_SKIP_VECTOR
     if (false) {
@@ -871,48 +974,48 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
       unsigned int cnt32[BINS];
 #pragma unroll
       for (int i = 0; i < BINS; i++) cnt32[i] = 0;
-      for (int i0 = tid; i0 < nvec; i0 += UN * nt) {
-        uint4 bgv[UN], gv[UN], lv[UN];
+      // the sweep count is a compile-time constant (NV vectors, NT threads, UN per sweep): fully unrolled, the batch requested one
+      // sweep ahead is renamed instead of copied, and every bound test but the last sweep's folds away
+      constexpr int NV = (int)(tpx / 16), SWEEPS = (NV + UN * NT - 1) / (UN * NT);
+      if (nvec) {
+        static_for<0, SWEEPS>([&](auto TI) {
+          constexpr int t = decltype(TI)::value;
+          uint4 bgv[UN], gv[UN], lv[UN];
 #pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const int i = i0 + u * nt;
-          bgv[u] = bgn[u]; gv[u] = gn[u];
-          lv[u] = make_uint4(labc, labc, labc, labc);
-          if (i < nvec && multi) { const int4 t = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(t.x, t.y, t.z, t.w); }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const int i = i0 + (UN + u) * nt;
-          gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-          if (i < nvec) {
-            if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
-            if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+          for (int u = 0; u < UN; u++) {
+            const int i = tid + (t * UN + u) * NT;
+            bgv[u] = bgn[u]; gv[u] = gn[u];
+            lv[u] = make_uint4(labc, labc, labc, labc);
+            if (i < NV && multi) { const int4 q = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(q.x, q.y, q.z, q.w); }
           }
-        }
-        if (do_conf) {
+          if constexpr (t + 1 < SWEEPS) {
 #pragma unroll
-          for (int u = 0; u < UN; u += 2) {
-            const unsigned int gw[8] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w, gv[u + 1].x, gv[u + 1].y, gv[u + 1].z, gv[u + 1].w};
-            const unsigned int lw8[8] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w, lv[u + 1].x, lv[u + 1].y, lv[u + 1].z, lv[u + 1].w};
-            bitslice_count<C>(gw, lw8, cnt32);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const int i = i0 + u * nt;
-          if (i < nvec && has_label) {
-            uint4 o = lv[u];
-            if (has_bg) {
-              const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
-              const unsigned int bw[4] = {bgv[u].x, bgv[u].y, bgv[u].z, bgv[u].w};
-              unsigned int ow[4];
-#pragma unroll
-              for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
-              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            for (int u = 0; u < UN; u++) {
+              const int i = tid + ((t + 1) * UN + u) * NT;
+              gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+              if (i < NV) {
+                if (has_bg) bgn[u] = __ldg(reinterpret_cast<const uint4*>(p.bg + base) + i);
+                if (do_conf) gn[u] = __ldg(reinterpret_cast<const uint4*>(p.gt + base) + i);
+              }
             }
-            reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
           }
-        }
+          if (do_conf) {
+#pragma unroll
+            for (int u = 0; u < UN; u += 2) {
+              const unsigned int gw[8] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w, gv[u + 1].x, gv[u + 1].y, gv[u + 1].z, gv[u + 1].w};
+              const unsigned int lw8[8] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w, lv[u + 1].x, lv[u + 1].y, lv[u + 1].z, lv[u + 1].w};
+              bitslice_count<C>(gw, lw8, cnt32);
+            }
+          }
+          if (has_label) {
+            if (has_bg) static_bg_overwrite4(lv, bgv, m4, bgl4);  // slots beyond NV hold masks of an earlier sweep or zeros
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+              const int i = tid + (t * UN + u) * NT;
+              if (i < NV) reinterpret_cast<uint4*>(p.label_out + base)[i] = lv[u];
+            }
+          }
+        });
       }
       if (do_conf) {
 #pragma unroll
@@ -1149,9 +1252,12 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
 
     if (multi && P >= 2) {
       float mxf;
-      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tid, nt);
-      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tid, nt);
-      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tid, nt);
+      int tidr[G];
+#pragma unroll
+      for (int q = 0; q < G; q++) tidr[q] = tid;
+      if (P == 2) mxf = static_prepass<C, G, VPG, 1>(g, vb, cls, ymap_s, tidr, nt);
+      else if (P == 3) mxf = static_prepass<C, G, VPG, 2>(g, vb, cls, ymap_s, tidr, nt);
+      else mxf = static_prepass<C, G, VPG, (C >= 4 ? 3 : 1)>(g, vb, cls, ymap_s, tidr, nt);
       const unsigned int mx = __reduce_max_sync(0xffffffffu, __float_as_uint(mxf));
       if ((tid & 31) == 0) atomicMax(&ctl->maxbits[b], mx);
     }
@@ -1359,20 +1465,12 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
             bitslice_count<C>(gw, lw8, cnt32);
           }
         }
+        if (has_label) {
+          if (has_bg) static_bg_overwrite4(lv, bgv, m4, bgl4);  // lanes beyond nvec hold zero masks
 #pragma unroll
-        for (int u = 0; u < UN; u++) {
-          const int i = i0 + u * nt;
-          if (i < nvec && has_label) {
-            uint4 o = lv[u];
-            if (has_bg) {
-              const unsigned int lw[4] = {lv[u].x, lv[u].y, lv[u].z, lv[u].w};
-              const unsigned int bw[4] = {bgv[u].x, bgv[u].y, bgv[u].z, bgv[u].w};
-              unsigned int ow[4];
-#pragma unroll
-              for (int q = 0; q < 4; q++) { const unsigned int eq = __vcmpeq4(bw[q], m4); ow[q] = (bgl4 & eq) | (lw[q] & ~eq); }
-              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            }
-            reinterpret_cast<uint4*>(p.label_out + base)[i] = o;
+          for (int u = 0; u < UN; u++) {
+            const int i = i0 + u * nt;
+            if (i < nvec) reinterpret_cast<uint4*>(p.label_out + base)[i] = lv[u];
           }
         }
       }

@@ -8,10 +8,10 @@ def find(pat, start=0):
     for i in range(start, len(src)):
         if pat in src[i]: return i + 1
     raise KeyError(pat)
-marks = [("head/tables", 1), ("load_h", find("void static_load_h")), ("rows", find("void static_rows")), ("prepass", find("float static_prepass")),
+marks = [("head/tables", 1), ("load_h", find("void static_load_h")), ("rows", find("unsigned int static_rows(")), ("recheck", find("unsigned int static_recheck4")), ("prepass", find("float static_prepass")),
          ("export", find("float static_div_slow")), ("kernel setup", find("void __launch_bounds__")), ("producer", find("===== producer warp")),
          ("export dispatch", find("auto export_units")), ("tile head", find("const bool is_export")), ("exact pass", find("auto exact_warp")),
-         ("vector pass", find("// ---- vector pass")), ("tile tail", find("}  // !is_export")), ("host", find("// host side"))]
+         ("vector pass", find("// ---- vector pass")), ("tile tail", find("}  // !is_export")), ("duo", find("constexpr int kDThreads")), ("host", find("// host side"))]
 out = subprocess.run(f"ncu -i {rep} --page source --csv --print-source cuda,sass", shell=True, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur = None; hd = None; agg = {}
