@@ -499,53 +499,73 @@ __device__ __forceinline__ float static_div_views(float a, float rcp_v, float fV
 // shared-memory address of the lane's left / right tap in row 0 of class 0 of each view.  The views of a group (a scale and its
 // flipped twin) share every constant, so they run through the same code (a two-trip loop); the sum starts from -0.f, the
 // identity of IEEE addition, so that the first view needs no special case.
-template <int C, int G, int VPG, int RPU, int E>
-__device__ __forceinline__ void static_export_unit(float* out_n, int c, const uint32_t (&sA)[G * VPG], const uint32_t (&sB)[G * VPG],
+// first / last source row a row group touches, and the widest span over the row groups (the shared hlerp code loads that many)
+__host__ __device__ constexpr int lo_imin(int h, int RPU, int E) { return lo_i0(h, RPU * E); }
+__host__ __device__ constexpr int lo_span(int h, int RPU, int E) { return lo_i1(h, RPU * E + RPU - 1) - lo_i0(h, RPU * E) + 1; }
+__host__ __device__ constexpr int lo_span_max(int h, int RPU) { int m = 0; for (int E = 0; E < 32 / RPU; E++) m = lo_span(h, RPU, E) > m ? lo_span(h, RPU, E) : m; return m; }
+
+// One unit = (class c, row group e = low-resolution rows RPU e .. RPU e + RPU - 1).  The unit code used to exist once per row group
+// (every offset and weight an immediate): 4 x 4.6 KB that the 13 warps of a CTA run side by side, and with the unrolled row loops
+// the tile loop outgrew the SM's 32 KB instruction cache -- 56 % of the export's stall samples were instruction fetches
+// (profiles/r02).  Now the horizontal interpolation of the source rows -- two thirds of the unit -- is ONE copy that addresses
+// [lane base + row-group offset + immediate]; only the vertical interpolation (which source rows feed which low-resolution row, with
+// which weights) is switched on e.  The operations and their order per sample are unchanged (bit-exact).
+template <int C, int G, int VPG, int RPU>
+__device__ __forceinline__ void static_export_unit(float* out_n, int c, int e, const uint32_t (&sA)[G * VPG], const uint32_t (&sB)[G * VPG],
                                                    const float (&lx0)[G], const float (&lx1)[G], float rcp_v, float fV) {
+  constexpr int NE = 32 / RPU;
   float a[RPU];
 #pragma unroll
-  for (int r = 0; r < RPU; r++) a[r] = -0.f;
+  for (int r = 0; r < RPU; r++) a[r] = 0.f;
   static_for<0, G>([&](auto GI) {
     constexpr int gi = decltype(GI)::value, h = st_h(G, gi), PL = 4 * h * h, RB = 4 * h;
-    constexpr int imin = lo_i0(h, RPU * E), imax = lo_i1(h, RPU * E + RPU - 1);
+    constexpr int J = lo_span_max(h, RPU);  // rows loaded (a row group with a shorter span loads a row it does not use)
+    int imin = 0;
+    static_for<1, NE>([&](auto EI) { constexpr int E = decltype(EI)::value; imin = e == E ? lo_imin(h, RPU, E) : imin; });
+    const uint32_t off = (uint32_t)(c * PL) + (uint32_t)imin * RB;
     if constexpr (VPG == 2) {
-      // a scale and its flipped twin: the two samples ride in the two lanes of the packed f32x2 operations (each lane is the
-      // same IEEE operation as the scalar code), the two adds of the view-order sum stay scalar and sequential
-      const uint32_t b0 = sA[2 * gi] + (uint32_t)(c * PL), b1 = sB[2 * gi] + (uint32_t)(c * PL);
-      const uint32_t t0 = sA[2 * gi + 1] + (uint32_t)(c * PL), t1 = sB[2 * gi + 1] + (uint32_t)(c * PL);
+      // a scale and its flipped twin ride in the two lanes of the packed f32x2 operations (each lane is the same IEEE operation
+      // as the scalar code); the two adds of the view-order sum stay scalar and sequential
+      const uint32_t b0 = sA[2 * gi] + off, b1 = sB[2 * gi] + off, t0 = sA[2 * gi + 1] + off, t1 = sB[2 * gi + 1] + off;
       const u64 LX0 = pack2(lx0[gi], lx0[gi]), LX1 = pack2(lx1[gi], lx1[gi]);
-      u64 Hr[imax - imin + 1];
-      static_for<imin, imax + 1>([&](auto II) {
-        constexpr int i = decltype(II)::value;
-        Hr[i - imin] = fma2(LX0, pack2(lds_f32_o<i * RB>(b0), lds_f32_o<i * RB>(t0)), mul2(LX1, pack2(lds_f32_o<i * RB>(b1), lds_f32_o<i * RB>(t1))));
+      u64 Hr[J];
+      static_for<0, J>([&](auto JI) {
+        constexpr int j = decltype(JI)::value;
+        Hr[j] = fma2(LX0, pack2(lds_f32_o<j * RB>(b0), lds_f32_o<j * RB>(t0)), mul2(LX1, pack2(lds_f32_o<j * RB>(b1), lds_f32_o<j * RB>(t1))));
       });
-      static_for<0, RPU>([&](auto RI) {
-        constexpr int r = decltype(RI)::value, ly = RPU * E + r;
-        constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
-        float ua, ub;
-        unpack2(fma2(pack2(l0, l0), Hr[lo_i0(h, ly) - imin], mul2(pack2(l1, l1), Hr[lo_i1(h, ly) - imin])), ua, ub);
-        a[r] = __fadd_rn(__fadd_rn(a[r], ua), ub);
+      static_for<0, NE>([&](auto EI) {
+        constexpr int E = decltype(EI)::value;
+        if (e == E) {
+          static_for<0, RPU>([&](auto RI) {
+            constexpr int r = decltype(RI)::value, ly = RPU * E + r;
+            constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
+            float ua, ub;
+            unpack2(fma2(pack2(l0, l0), Hr[lo_i0(h, ly) - lo_imin(h, RPU, E)], mul2(pack2(l1, l1), Hr[lo_i1(h, ly) - lo_imin(h, RPU, E)])), ua, ub);
+            a[r] = gi == 0 ? __fadd_rn(ua, ub) : __fadd_rn(__fadd_rn(a[r], ua), ub);
+          });
+        }
       });
     } else {
-#pragma unroll 1
-      for (int tw = 0; tw < VPG; tw++) {
-        const uint32_t b0 = (tw ? sA[gi * VPG + VPG - 1] : sA[gi * VPG]) + (uint32_t)(c * PL);
-        const uint32_t b1 = (tw ? sB[gi * VPG + VPG - 1] : sB[gi * VPG]) + (uint32_t)(c * PL);
-        float Hr[imax - imin + 1];
-        static_for<imin, imax + 1>([&](auto II) {
-          constexpr int i = decltype(II)::value;
-          Hr[i - imin] = __fmaf_rn(lx0[gi], lds_f32_o<i * RB>(b0), __fmul_rn(lx1[gi], lds_f32_o<i * RB>(b1)));
-        });
-        static_for<0, RPU>([&](auto RI) {
-          constexpr int r = decltype(RI)::value, ly = RPU * E + r;
-          constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
-          const float u = __fmaf_rn(l0, Hr[lo_i0(h, ly) - imin], __fmul_rn(l1, Hr[lo_i1(h, ly) - imin]));
-          a[r] = __fadd_rn(a[r], u);
-        });
-      }
+      const uint32_t b0 = sA[gi] + off, b1 = sB[gi] + off;
+      float Hr[J];
+      static_for<0, J>([&](auto JI) {
+        constexpr int j = decltype(JI)::value;
+        Hr[j] = __fmaf_rn(lx0[gi], lds_f32_o<j * RB>(b0), __fmul_rn(lx1[gi], lds_f32_o<j * RB>(b1)));
+      });
+      static_for<0, NE>([&](auto EI) {
+        constexpr int E = decltype(EI)::value;
+        if (e == E) {
+          static_for<0, RPU>([&](auto RI) {
+            constexpr int r = decltype(RI)::value, ly = RPU * E + r;
+            constexpr float l1 = lo_l1(h, ly), l0 = 1.f - l1;
+            const float u = __fmaf_rn(l0, Hr[lo_i0(h, ly) - lo_imin(h, RPU, E)], __fmul_rn(l1, Hr[lo_i1(h, ly) - lo_imin(h, RPU, E)]));
+            a[r] = gi == 0 ? u : __fadd_rn(a[r], u);
+          });
+        }
+      });
     }
   });
-  float* outp = out_n + (c * kSLow + RPU * E) * kSLow + (threadIdx.x & 31);
+  float* outp = out_n + (c * kSLow + RPU * e) * kSLow + (threadIdx.x & 31);
   // a / V: the arithmetic of static_div_views, two rows per packed operation; one range test for the whole unit
   float lo = fabsf(a[0]), hi = lo;
 #pragma unroll
@@ -749,10 +769,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
       }
       if (u >= UNITS) break;
       const int c = u / kSNE, e = u - c * kSNE;
-      static_for<0, kSNE>([&](auto EI) {
-        constexpr int E = decltype(EI)::value;
-        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(out_n, c, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
-      });
+      static_export_unit<C, G, VPG, kSLow / kSNE>(out_n, c, e, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
       u += g.cwarps;
     }
   };
@@ -778,6 +795,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     const int n = ctl->tile[sb];
     if (n < 0) break;
     const int4 hd = lds_i4(smem_u32(&ctl->head[sb]));
+    const int ctl_single = hd.y;
     uint32_t vb[V];
 #pragma unroll
     for (int v = 0; v < V; v++) vb[v] = smem_u32(vsm) + 4u * (uint32_t)(sb * g.buf_floats + g.view_off[v]) + ((((unsigned)hd.w >> (2 * v)) & 3u) << 2);
@@ -1037,7 +1055,9 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     }
     }  // !is_export
 #ifndef PISTO_X_SKIP_EXPORT
-    if (need_low) export_units(n, sb, vb);
+    // With export warps (g.aux > 0) the compute warps leave the units of a multi-label tile to them -- the export warps have the
+    // whole row loop's time for it and release the staging buffer when they are done -- and help only on single-label tiles.
+    if (need_low && (is_export || g.aux == 0 || ctl_single >= 0)) export_units(n, sb, vb);
 #endif
     __syncwarp();
     if (NB == 2 && (tid & 31) == 0) mbar_arrive(&ctl->empty[sb]);
@@ -1208,10 +1228,7 @@ __global__ void __launch_bounds__(kDThreads, 2) fuse_duo_kernel(const __grid_con
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u >= UNITS) break;
       const int c = u / kSNE, e = u - c * kSNE;
-      static_for<0, kSNE>([&](auto EI) {
-        constexpr int E = decltype(EI)::value;
-        if (e == E) static_export_unit<C, G, VPG, kSLow / kSNE, E>(out_n, c, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
-      });
+      static_export_unit<C, G, VPG, kSLow / kSNE>(out_n, c, e, sA, sB, lx0, lx1, p.dec.rcp_v, p.dec.fV);
     }
   };
 
@@ -1570,7 +1587,7 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   g->queue_off = off; off += 4 * kFQueueCap;
   g->lab_off = off; off += kST * kST;
   off = (off + 127) & ~127;
-  g->views_off = off; off += nbuf * 4 * fl;
+  g->views_off = off; off += nbuf * 4 * fl + 256;  // slack: the export's shared row loads may touch one row past the last view
   g->smem_bytes = off;
   return off <= h->smem_optin - 1024;
 }
@@ -1592,7 +1609,7 @@ static bool make_duo_geom(const pisto_ctx* h, const FuseParams& p, StaticGeom* g
   g->queue_off = off; off += 4 * kDQueueCap;
   g->lab_off = off; off += kST * kSGX;
   off = (off + 127) & ~127;
-  g->views_off = off; off += 4 * g->buf_floats + 64;  // slack: nothing reads past the last view, but keep the export's immediate offsets in bounds
+  g->views_off = off; off += 4 * g->buf_floats + 256;  // slack: the export's shared row loads may touch one row past the last view
   g->smem_bytes = off;
   return 2 * (off + 1024) <= 233472;
 }

@@ -15,7 +15,7 @@ def rep(t, n):
     return t.to(dev).repeat((r,) + (1,) * (t.dim() - 1))[:n].contiguous()
 
 
-def timeit(fn, steps=10, warmup=3):
+def timeit(fn, steps=30, warmup=3):
     for _ in range(warmup): fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
