@@ -92,6 +92,9 @@ constexpr int kSU2 = PISTO_SU2;  // ... for two / three fields (code size: the i
 #endif
 constexpr int kSAux = PISTO_SAUX;  // warps that only work on the 32x32 export
 constexpr int kSNE = PISTO_SNE;  // export units per class (each 32 / kSNE low-resolution rows)
+#ifndef PISTO_STATIC_MASKS_AHEAD
+#define PISTO_STATIC_MASKS_AHEAD 1
+#endif
 
 struct StaticGeom {
   float wtab[kSR][4];                // -l0 of group g on row r of a strip (the unrolled-by-8 row loop reads it through uniform loads)
@@ -840,11 +843,14 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     const long long vbase_px = (long long)n * tpx;
     const bool vec_ok = ((((uintptr_t)p.bg | (uintptr_t)p.gt | (uintptr_t)p.label_out) & 15) == 0);
     const int nvec = vec_ok ? (int)(tpx / 16) : 0;
-    uint4 bgn[UN], gn[UN];
+    // every sweep of the vector pass is requested at once (SWEEPS * UN 16-byte vectors per mask and thread): the row loop's registers
+    // are free by then, and a request made one sweep ahead only had ~100 instructions to cover an L2 round trip
+    constexpr int NV = (int)(tpx / 16), SWEEPS = (NV + UN * NT - 1) / (UN * NT), NM = PISTO_STATIC_MASKS_AHEAD ? SWEEPS * UN : UN;
+    uint4 bgn[NM], gn[NM];
     auto request_masks = [&]() {
 #pragma unroll
-      for (int u = 0; u < UN; u++) {
-        const int i = tid + u * nt;
+      for (int u = 0; u < NM; u++) {
+        const int i = tid + u * NT;
         gn[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         bgn[u] = make_uint4(0u, 0u, 0u, 0u);
         if (i < nvec) {
@@ -994,19 +1000,19 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
       for (int i = 0; i < BINS; i++) cnt32[i] = 0;
       // the sweep count is a compile-time constant (NV vectors, NT threads, UN per sweep): fully unrolled, the batch requested one
       // sweep ahead is renamed instead of copied, and every bound test but the last sweep's folds away
-      constexpr int NV = (int)(tpx / 16), SWEEPS = (NV + UN * NT - 1) / (UN * NT);
       if (nvec) {
         static_for<0, SWEEPS>([&](auto TI) {
           constexpr int t = decltype(TI)::value;
+          constexpr int mb = PISTO_STATIC_MASKS_AHEAD ? t * UN : 0;
           uint4 bgv[UN], gv[UN], lv[UN];
 #pragma unroll
           for (int u = 0; u < UN; u++) {
             const int i = tid + (t * UN + u) * NT;
-            bgv[u] = bgn[u]; gv[u] = gn[u];
+            bgv[u] = bgn[mb + u]; gv[u] = gn[mb + u];
             lv[u] = make_uint4(labc, labc, labc, labc);
             if (i < NV && multi) { const int4 q = lds_i4(lab_s + 16u * i); lv[u] = make_uint4(q.x, q.y, q.z, q.w); }
           }
-          if constexpr (t + 1 < SWEEPS) {
+          if constexpr (t + 1 < SWEEPS && !PISTO_STATIC_MASKS_AHEAD) {
 #pragma unroll
             for (int u = 0; u < UN; u++) {
               const int i = tid + ((t + 1) * UN + u) * NT;
