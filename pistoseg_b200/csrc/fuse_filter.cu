@@ -9,6 +9,7 @@ int pisto_launch_filter_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, i
 int pisto_launch_static_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh
 int pisto_launch_static_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 int pisto_launch_narrow_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);  // fuse_static.cuh, 2 columns per thread
+int pisto_launch_narrow_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);
 int pisto_launch_duo_c3(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched);     // fuse_static.cuh, two CTAs per SM
 
 // np: column pairs per thread to use (1 or 2), 0 = pick (automatic dispatch: the shape-specialised kernel of fuse_static.cuh
@@ -24,21 +25,16 @@ int pisto_launch_fuse_filter(pisto_ctx* h, const FuseParams& p, cudaStream_t st,
   if (bytes & 1) return PISTO_OK;
   bool views_aligned = true;
   for (int v = 0; v < p.V; v++) views_aligned &= ((uintptr_t)p.view[v].logits & 15) == 0;  // TMA source spans need a 16-byte aligned allocation start
-  if ((np == 0 || np == 4) && views_aligned && p.C == 3) {
-    static const bool no_duo = getenv("PISTO_NO_DUO") != nullptr;  // A/B knob
-    int rc = PISTO_OK;
-    // automatic dispatch: the single-view set (BASELINE config 1) only -- there two CTAs per SM measure +10 %; with three scale groups
-    // the one-CTA kernel below is faster (profiles/r02)
-    if (np == 4 || (!no_duo && p.V == 1)) rc = pisto_launch_duo_c3(h, p, st, launched);
-    if (rc != PISTO_OK || *launched || np == 4) return rc;
+  if (np == 4) return (views_aligned && p.C == 3) ? pisto_launch_duo_c3(h, p, st, launched) : PISTO_OK;  // explicit only: the one-CTA kernel measures faster (profiles/r02)
+  if (np == 5) {
+    if (!views_aligned) return PISTO_OK;
+    return p.C == 3 ? pisto_launch_narrow_c3(h, p, st, launched) : (p.C == 4 ? pisto_launch_narrow_c4(h, p, st, launched) : PISTO_OK);
   }
-  if (np == 4) return PISTO_OK;
-  if (np == 5) return (views_aligned && p.C == 3) ? pisto_launch_narrow_c3(h, p, st, launched) : PISTO_OK;
   if ((np == 0 || np == 3) && views_aligned) {
     static const bool no_static = getenv("PISTO_NO_STATIC") != nullptr;  // A/B knob
     int rc = PISTO_OK;
     // automatic dispatch: where it is measured faster than the generic kernel (C = 3, three scales x flip); always when asked for
-    if (np == 3 || (!no_static && p.V == 6)) {
+    if (np == 3 || (!no_static && (p.V == 6 || p.V == 1))) {
       if (p.C == 3) rc = pisto_launch_static_c3(h, p, st, launched);
       else if (p.C == 4) rc = pisto_launch_static_c4(h, p, st, launched);
     }

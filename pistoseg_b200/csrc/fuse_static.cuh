@@ -791,6 +791,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
   constexpr long long tpx = (long long)kST * kST;
   constexpr int NT = 32 * ((GX * kSS + 31) / 32);  // compute threads (= ncomp)
 
+
   for (int k = 0;; k++) {
     const int b = k & 1;
     const int sb = NB == 2 ? b : 0;

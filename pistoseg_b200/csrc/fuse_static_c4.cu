@@ -9,3 +9,10 @@ int pisto_launch_static_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, b
   }
   return PISTO_OK;
 }
+
+// 2 columns per thread, 26 warps per SM (fuse_narrow_kernel): three difference fields fit the registers without spilling
+int pisto_launch_narrow_c4(pisto_ctx* h, const FuseParams& p, cudaStream_t st, bool* launched) {
+  const int f = pisto_filter_flags(p);
+  if (p.V == 6 && f == 18) return launch_narrow<4, 3, 2, 18, 1>(h, p, st, launched);
+  return PISTO_OK;
+}

@@ -14,9 +14,10 @@ res = {
     "shared_memory_wavefronts_frac": get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100,
     "fma_pipe_frac": get("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active") / 100,
     "alu_pipe_frac": get("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active") / 100,
+    "mufu_pipe_frac": get("sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active") / 100,
     "dram_throughput_frac_under_ncu": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") / 100,
     "warps_per_sm": get("sm__warps_active.avg.pct_of_peak_sustained_active") / 100 * 64,
-    "binding": "instruction issue / dependent-instruction latency at 16 warps per SM (registers and shared memory allow no more); see DESIGN.md 4.1",
+    "binding": "instruction issue / dependent-instruction latency at 14 warps per SM (128 registers x 448 threads, 202 KB shared memory: one CTA); see DESIGN.md 4.1",
     "source": note,
 }
 tj = {"kernel": vals[hdr.index("Kernel Name")], "tiles_per_launch": tiles, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
