@@ -29,6 +29,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// the same probe with a suspend-time hint: the hardware parks the thread until the phase completes or ~ns nanoseconds have passed,
+// instead of returning after its (short) default limit -- a waiting warp then issues almost nothing
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded spin: a lost TMA must surface as a launch failure, never as a hung GPU
 #pragma unroll 1
@@ -41,9 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // same, for a lone waiter that should not compete for issue slots with the warps doing the work
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
-  for (int it = 0; it < (1 << 24); it++) {
+  for (int it = 0; it < (1 << 22); it++) {
+#ifdef PISTO_SPIN_PRODUCER
     if (mbar_try_wait(bar, parity)) return;
     __nanosleep(1000);
+#else
+    if (mbar_try_wait_hint(bar, parity, 20000u)) return;
+#endif
   }
   __trap();
 }
