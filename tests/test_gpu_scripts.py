@@ -14,6 +14,8 @@ from oracle import fuse as ofuse
 from oracle import stitch as ostitch
 from oracle import tta as otta
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 
@@ -233,3 +235,60 @@ def test_stitch_rejects_crops_larger_than_the_tile(cuda):
             ops.stitch_accumulate(tiles, bad, canvas, count)
     ops.stitch_accumulate(tiles, [[0, 0, 8, 8], [8, 8, 5, 3]], canvas, count)
 
+
+
+def test_oeem_prepare_seg_inputs_script(cuda, tmp_path):
+    """OEEM/classification/prepare_seg_inputs.py (drop-in for the reference script of the same path): configuration file, output directory
+    and file names are the reference's; every ``.npy`` equals the oracle's restatement of prepare_seg_inputs.py:96-137 on the same CAMs
+    bit for bit.  Dataset and classifier are stubs with the reference modules' interfaces (TrainingSetCAM item layout, forward_cam)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oeem_prepare_seg_inputs", os.path.join(ROOT, "OEEM", "classification", "prepare_seg_inputs.py"))
+    script = importlib.util.module_from_spec(spec); spec.loader.exec_module(script)
+    from pistoseg_b200 import oeem
+    root = tmp_path
+    (root / "classification").mkdir()
+    (root / "classification" / "configuration_wsss4luad.yml").write_text(
+        "---\nside_length: 224\nstride: 74\nnum_of_class: 3\nmean: [0.485, 0.456, 0.406]\nstd: [0.229, 0.224, 0.225]\nscales: [1, 1.5, 2]\nnetwork_image_size: 224\n")
+    scales, side, stride = [1, 1.5, 2], 224, 74
+    sizes = {"437-[1, 0, 1].png": (300, 260), "12-[0, 1, 1].png": (150, 400)}   # (rows, cols)
+
+    class Stub(torch.utils.data.Dataset):   # dataset.TrainingSetCAM.__getitem__ (dataset.py:76-87)
+        def __init__(self):
+            self.files = sorted(sizes)
+        def __len__(self):
+            return len(self.files)
+        def __getitem__(self, i):
+            name = self.files[i]
+            w, h = sizes[name]
+            g = torch.Generator().manual_seed(i)
+            ims, poss = [], []
+            for s in scales:
+                pos = oeem.online_cut_positions(int(w * s), int(h * s), side, stride)
+                ims.append([torch.randn((3, 224, 224), generator=g) for _ in pos])
+                poss.append([(np.int64(y), np.int64(x)) for y, x in pos])
+            return name, ims, poss, scales, np.array([1, 0, 1])
+
+    class Net(torch.nn.Module):             # network.wide_resnet.wideResNet.forward_cam: [n,3,224,224] -> [n,C,28,28]
+        def __init__(self):
+            super().__init__()
+            self.mix = torch.nn.Conv2d(3, 3, 1)
+        def forward_cam(self, x):
+            return self.mix(torch.nn.functional.avg_pool2d(x, 8))
+
+    torch.manual_seed(3)
+    net = Net().to(cuda).eval()
+    args = types.SimpleNamespace(batch=5, device=[cuda.index or 0], ckpt="res38d.pth", dataset="wsss4luad")
+    n = script.main(args, net_cam=net, dset=Stub(), root=str(root), image_wh=lambda name: sizes[name], progress=False)
+    assert n == 2
+    out_dir = root / "classification" / "wsss4luad-res38d_train_pseudo_mask"
+    assert sorted(os.listdir(out_dir)) == ["12-[0, 1, 1].npy", "437-[1, 0, 1].npy"]
+    ds = Stub()
+    for i, name in enumerate(ds.files):
+        _, ims, poss, _, _ = ds[i]
+        with torch.no_grad():
+            cams = [torch.cat([net.forward_cam(b.to(cuda)) for b in torch.split(torch.stack(l), 5)]).cpu() for l in ims]
+        pos = [[(int(y), int(x)) for y, x in p] for p in poss]
+        ref = ostitch.cam_to_32(ostitch.cam_ensemble(cams, pos, scales, sizes[name], side=side))
+        got = np.load(out_dir / (name[:-4] + ".npy"))
+        assert got.dtype == np.float64 and got.shape == (3, 32, 32)
+        assert np.array_equal(got, ref)
