@@ -152,7 +152,14 @@ template <int N> __device__ __forceinline__ float minabs(const float (&a)[N]) {
 // differences; the result is trusted (return value) only when every one of those quantities is further than tau from
 // zero, which implies the best candidate leads every other one by more than tau.  c4[k] = 0x01010101 * cls[k].
 template <int K, int NP>
+__device__ __forceinline__ float labels_from_diffs_min(const u64 (&acc)[K][NP], const unsigned int (&c4)[4], unsigned int& lab4);
+template <int K, int NP>
 __device__ __forceinline__ bool labels_from_diffs(const u64 (&acc)[K][NP], const unsigned int (&c4)[4], float tau, unsigned int& lab4) {
+  return labels_from_diffs_min<K, NP>(acc, c4, lab4) > tau;
+}
+// the same, returning the smallest |quantity| instead of testing it (the caller may fold several rows into one test)
+template <int K, int NP>
+__device__ __forceinline__ float labels_from_diffs_min(const u64 (&acc)[K][NP], const unsigned int (&c4)[4], unsigned int& lab4) {
   float d[K][2 * NP];
 #pragma unroll
   for (int k = 0; k < K; k++)
@@ -185,7 +192,7 @@ __device__ __forceinline__ bool labels_from_diffs(const u64 (&acc)[K][NP], const
     lab4 = (c4[0] & m0) | (c4[1] & m1) | (c4[2] & m2) | (c4[3] & ~(m0 | m1 | m2));
     mn = fminf(fminf(fminf(minabs(d[0]), minabs(d[K > 1 ? 1 : 0])), fminf(minabs(d[K > 2 ? 2 : 0]), minabs(e12))), fminf(minabs(e13), minabs(e23)));
   }
-  return mn > tau;
+  return mn;
 }
 
 // rare path: which of the thread's pixels really fail the lead test (top-2 gap of the candidates <= tau)

@@ -92,6 +92,13 @@ constexpr int kSU2 = PISTO_SU2;  // ... for two / three fields (code size: the i
 #endif
 constexpr int kSAux = PISTO_SAUX;  // warps that only work on the 32x32 export
 constexpr int kSNE = PISTO_SNE;  // export units per class (each 32 / kSNE low-resolution rows)
+#ifndef PISTO_STATIC_W3
+#define PISTO_STATIC_W3 1  // row loops with one difference field (or one scale group and two fields) keep three-tap column weights in registers (0 = select form)
+#endif
+#ifndef PISTO_SMR
+#define PISTO_SMR 1
+#endif
+constexpr int kSMR = PISTO_SMR;  // rows whose lead test is folded into one comparison (1, 2 or 4; must divide the unroll factors)
 #ifndef PISTO_STATIC_MASKS_AHEAD
 #define PISTO_STATIC_MASKS_AHEAD 1
 #endif
@@ -137,6 +144,47 @@ __device__ __forceinline__ void static_load_h(uint32_t a, const float4 L1, unsig
   }
 }
 
+// The same interpolation without per-column selects: the 4 columns of a thread take their two taps from the 3 adjacent cells y0, y1, y2,
+// so every column is w_a y0 + w_b y1 + w_c y2 with (w_a, w_b, w_c) = (l0, l1, 0) or (0, l0, l1) -- three packed multiply-adds per column
+// pair with the cell value broadcast to both lanes, instead of six selects and three predicate set-ups.  One of the three weights is an
+// exact zero, the other two terms are rounded as before (a product, then one fma): the error bound of DESIGN.md 4.1 is unchanged.
+// (Tiles with non-finite logits never reach the row loop, so 0 x Inf cannot occur.)
+struct ColWeights3 { u64 a[2], b[2], c[2]; };  // [column pair]
+__device__ __forceinline__ ColWeights3 static_weights3(const float4 L1, unsigned int sel) {
+  const float l1[4] = {L1.x, L1.y, L1.z, L1.w};
+  float wa[4], wb[4], wc[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const float l0 = __fsub_rn(1.f, l1[c]);
+    const bool d = (sel >> c) & 1u;
+    wa[c] = d ? 0.f : l0; wb[c] = d ? l0 : l1[c]; wc[c] = d ? l1[c] : 0.f;
+  }
+  ColWeights3 w;
+  w.a[0] = pack2(wa[0], wa[1]); w.a[1] = pack2(wa[2], wa[3]);
+  w.b[0] = pack2(wb[0], wb[1]); w.b[1] = pack2(wb[2], wb[3]);
+  w.c[0] = pack2(wc[0], wc[1]); w.c[1] = pack2(wc[2], wc[3]);
+  return w;
+}
+template <int K, int OFF>
+__device__ __forceinline__ void static_load_h3(uint32_t a, const ColWeights3& w, u64 (&H)[K][2]) {
+  float y0[K], y1[K], y2[K];
+  if constexpr (K == 1) {
+    y0[0] = lds_f32_o<OFF>(a); y1[0] = lds_f32_o<OFF + 4>(a); y2[0] = lds_f32_o<OFF + 8>(a);
+  } else if constexpr (K == 2) {
+    const float2 v0 = lds_f2_o<OFF>(a), v1 = lds_f2_o<OFF + 8>(a), v2 = lds_f2_o<OFF + 16>(a);
+    y0[0] = v0.x; y0[K - 1] = v0.y; y1[0] = v1.x; y1[K - 1] = v1.y; y2[0] = v2.x; y2[K - 1] = v2.y;
+  } else {
+    const float4 v0 = lds_f4_o<OFF>(a), v1 = lds_f4_o<OFF + 16>(a), v2 = lds_f4_o<OFF + 32>(a);
+    y0[0] = v0.x; y0[1 % K] = v0.y; y0[K - 1] = v0.z; y1[0] = v1.x; y1[1 % K] = v1.y; y1[K - 1] = v1.z;
+    y2[0] = v2.x; y2[1 % K] = v2.y; y2[K - 1] = v2.z;
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++)
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+      H[k][q] = fma2(w.c[q], pack2(y2[k], y2[k]), fma2(w.b[q], pack2(y1[k], y1[k]), mul2(w.a[q], pack2(y0[k], y0[k]))));
+}
+
 // ---- the 32 rows of one strip: blocks of U rows, each block fully unrolled -------------------------------------------------
 // U = 32: one block, every schedule decision and weight is a compile-time constant.  U = 8: four passes over the same code; a
 // refill site is unconditional when the group moves at that row of every block (h = 28), tested against a uniform bit mask
@@ -155,9 +203,10 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
   u64 Hb[G][K][2], Dh[G][K][2], base[K][2];
   uint32_t yb[G];  // address of the map row that holds Ha (cell of the thread's first column)
   unsigned int selm[G];
-  constexpr bool HOIST = K == 1;  // the horizontal weights of the thread's columns stay in registers (else: one 16-byte load per refill)
+  constexpr bool HOIST = PISTO_STATIC_W3 && (K == 1 || (G == 1 && K <= 2));  // the horizontal weights of the thread's columns stay in registers, in three-tap form (else: one 16-byte load per refill)
   float4 L1[G] = {};
-  auto l1_of = [&](int gi) { return HOIST ? L1[gi] : lds_f4(col4_t + gi * 16u * kSGX); };
+  ColWeights3 W3[HOIST ? G : 1];
+  auto l1_of = [&](int gi) { return lds_f4(col4_t + gi * 16u * kSGX); };
   static_for<0, G>([&](auto GI) {
     constexpr int gi = decltype(GI)::value, h = st_h(G, gi), RS = 4 * KP * (h + 2);
     const uint32_t u = lds_u32(col4i_t + gi * 4u * kSGX);
@@ -166,9 +215,15 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
     selm[gi] = u >> 16;
     L1[gi] = lds_f4(col4_t + gi * 16u * kSGX);
     u64 Ha[K][2];
-    static_load_h<K, 0>(yb[gi], L1[gi], selm[gi], Ha);
-    static_load_h<K, RS>(yb[gi], L1[gi], selm[gi], Hb[gi]);
-    if (!HOIST) L1[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (HOIST) {
+      W3[gi] = static_weights3(L1[gi], selm[gi]);
+      static_load_h3<K, 0>(yb[gi], W3[gi], Ha);
+      static_load_h3<K, RS>(yb[gi], W3[gi], Hb[gi]);
+    } else {
+      static_load_h<K, 0>(yb[gi], L1[gi], selm[gi], Ha);
+      static_load_h<K, RS>(yb[gi], L1[gi], selm[gi], Hb[gi]);
+    }
+    L1[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < K; k++)
 #pragma unroll
@@ -190,6 +245,7 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; blk++) {
     unsigned int unc_blk = 0;
+    float mnrun = 0.f;
     unsigned int advb[G];
 #pragma unroll
     for (int gi = 0; gi < G; gi++) advb[gi] = U == 32 ? 0u : g.adv[gi] >> (blk * U);
@@ -205,7 +261,8 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
           if (now) {
             yb[gi] += RS;
             u64 Hn[K][2];
-            static_load_h<K, RS>(yb[gi], l1_of(gi), selm[gi], Hn);
+            if constexpr (HOIST) static_load_h3<K, RS>(yb[gi], W3[gi], Hn);
+            else static_load_h<K, RS>(yb[gi], l1_of(gi), selm[gi], Hn);
 #pragma unroll
             for (int k = 0; k < K; k++)
 #pragma unroll
@@ -234,8 +291,12 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
           for (int gi = 0; gi < G; gi++) a = fma2(pack2(w[gi], w[gi]), Dh[gi][k][q], a);
           acc[k][q] = a;
         }
+      // the lead test of kSMR consecutive rows can be folded into one comparison (a failure flags all of them, the per-pixel recheck
+      // sorts it out); measured slower for kSMR = 4 / 8 (-6 % / -15 %: the rechecks sit on the critical path of the barrier), hence 1
       unsigned int lab4;
-      if (!labels_from_diffs<K, 2>(acc, c4, tau, lab4)) unc_blk |= 1u << rr;
+      const float mn = labels_from_diffs_min<K, 2>(acc, c4, lab4);
+      mnrun = (rr % kSMR == 0) ? mn : fminf(mnrun, mn);
+      if constexpr (rr % kSMR == kSMR - 1) { if (!(mnrun > tau)) unc_blk |= ((1u << kSMR) - 1u) << (rr - (kSMR - 1)); }
       if constexpr (PACK) sts_u8_o<rr * kSGX>(lab_a, (lab4 * 0x01100440u) >> 24);  // 2 bits per pixel, fields in the order (0, 2, 1, 3)
       else sts_u32_o<rr * kST>(lab_a, lab4);
     });
@@ -930,6 +991,8 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         }
       }
       if (unc) {
+        // (Measured and dropped: pushing the 4 pixels of a flagged row straight to the queue, without the in-thread recheck: -5 %.
+        // The recheck clears three of four pixels and overlaps with the other warps' rows; the exact pass runs between two barriers.)
         if (P == 2) static_push_rows<G, 1, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
         else if (P == 3) static_push_rows<G, 2, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
         else static_push_rows<G, (C >= 4 ? 3 : 1), NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
