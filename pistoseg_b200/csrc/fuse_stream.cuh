@@ -33,6 +33,36 @@
 
 namespace {
 
+// The same softmax for a pixel PAIR held in f32x2 lanes (the streaming kernels work on column pairs).  The MUFU unit (16 lanes per
+// clock and SM) is what bounds PROB_MEAN, so only the C exponentials per pixel stay on it: the reciprocal of the sum -- in [1, C] --
+// is a packed Newton iteration on the FMA pipe (integer-subtraction seed, relative error 0.12 -> 1.4e-2 -> 2e-4 -> 4e-8 after three
+// steps), and subtracting the maximum is folded into the scaling by log2(e): t = x * log2e - m * log2e (one packed fma per class).
+// Probabilities differ from pisto_softmax_fast by < 2e-7.
+template <int C>
+__device__ __forceinline__ void pisto_softmax_fast2(u64 (&u)[C]) {
+  float a0, a1, m0, m1;
+  unpack2(u[0], m0, m1);
+#pragma unroll
+  for (int c = 1; c < C; c++) { unpack2(u[c], a0, a1); m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); }
+  const u64 L2E = pack2(1.4426950408889634f, 1.4426950408889634f);
+  const u64 nm = mul2(pack2(-m0, -m1), L2E);
+  u64 sum = 0;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    unpack2(fma2(u[c], L2E, nm), a0, a1);
+    u[c] = pack2(pisto_ex2_approx(a0), pisto_ex2_approx(a1));
+    sum = c == 0 ? u[c] : add2(sum, u[c]);
+  }
+  unpack2(sum, a0, a1);
+  u64 r = pack2(__uint_as_float(0x7EF311C7u - __float_as_uint(a0)), __uint_as_float(0x7EF311C7u - __float_as_uint(a1)));
+  const u64 one = pack2(1.f, 1.f), ns = pack2(-a0, -a1);
+#pragma unroll
+  for (int it = 0; it < 3; it++) r = fma2(r, fma2(ns, r, one), r);
+#pragma unroll
+  for (int c = 0; c < C; c++) u[c] = mul2(u[c], r);
+}
+
+
 #ifndef PISTO_STREAM_THREADS
 #define PISTO_STREAM_THREADS 384
 #endif
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
       const long long tile_px = (long long)T_h * T_w;
       for (int k = 0;; k++) {
         const int b = k & 1;
-        if (k >= 2) mbar_wait(&ctl->empty[b], ((k >> 1) - 1) & 1);  // all compute warps are done with buffer b
+        if (k >= 2) mbar_wait_sleep(&ctl->empty[b], ((k >> 1) - 1) & 1);  // all compute warps are done with buffer b
         const int t = atomicAdd(g.counter, 1);
         const int tile = t < p.N ? t : -1;
         ctl->tile[b] = tile;
@@ -340,15 +370,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) fuse_stream_kernel(const __gri
           u64 u[C];
 #pragma unroll
           for (int c = 0; c < C; c++) u[c] = fma2(w.x, Ha[v][c], mul2(w.y, Hb[v][c]));
-          if (PROB) {
-            float s0[C], s1[C];
-#pragma unroll
-            for (int c = 0; c < C; c++) unpack2(u[c], s0[c], s1[c]);
-            pisto_softmax_fast<C>(s0);
-            pisto_softmax_fast<C>(s1);
-#pragma unroll
-            for (int c = 0; c < C; c++) u[c] = pack2(s0[c], s1[c]);
-          }
+          if (PROB) pisto_softmax_fast2<C>(u);
 #pragma unroll
           for (int c = 0; c < C; c++) acc[c] = (v == 0) ? u[c] : add2(acc[c], u[c]);
         }
