@@ -130,6 +130,9 @@ template <int NP> __device__ __forceinline__ void sts_px(uint32_t a, unsigned in
   else asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
 }
 
+#ifndef PISTO_K2_TOURNAMENT
+#define PISTO_K2_TOURNAMENT 1
+#endif
 #ifndef PISTO_K3_TOURNAMENT
 #define PISTO_K3_TOURNAMENT 1
 #endif
@@ -177,10 +180,22 @@ __device__ __forceinline__ float labels_from_diffs_min(const u64 (&acc)[K][NP], 
     float e12[2 * NP];
 #pragma unroll
     for (int q = 0; q < NP; q++) unpack2(sub2(acc[0][q], acc[K > 1 ? 1 : 0][q]), e12[2 * q], e12[2 * q + 1]);
+#if PISTO_K2_TOURNAMENT
+    // three candidates (0, D1, D2): m = max(D1, D2) plays 0; trusted when |m| and |D1 - D2| exceed tau (the winner then leads both
+    // others by more than tau).  Unlike the pairwise form it does not flag a pixel whose LOSING candidate happens to sit near 0.
+    float m[2 * NP];
+#pragma unroll
+    for (int j = 0; j < 2 * NP; j++) m[j] = fmaxf(d[0][j], d[K > 1 ? 1 : 0][j]);
+    const unsigned int nm = negmask<NP>(m), n12 = negmask<NP>(e12);
+    const unsigned int b = (c4[2] & n12) | (c4[1] & ~n12);
+    lab4 = (c4[0] & nm) | (b & ~nm);
+    mn = fminf(minabs(m), minabs(e12));
+#else
     const unsigned int n1 = negmask<NP>(d[0]), n2 = negmask<NP>(d[K > 1 ? 1 : 0]), n12 = negmask<NP>(e12);
     const unsigned int m0 = n1 & n2, m1 = ~n1 & ~n12;
     lab4 = (c4[0] & m0) | (c4[1] & m1) | (c4[2] & ~(m0 | m1));
     mn = fminf(fminf(minabs(d[0]), minabs(d[K > 1 ? 1 : 0])), minabs(e12));
+#endif
   } else {
 #if PISTO_K3_TOURNAMENT
     // four candidates (0, D1, D2, D3) as a two-round tournament instead of all six pairwise comparisons: m01 = max(0, D1) and
