@@ -93,7 +93,7 @@ constexpr int kSU2 = PISTO_SU2;  // ... for two / three fields (code size: the i
 constexpr int kSAux = PISTO_SAUX;  // warps that only work on the 32x32 export
 constexpr int kSNE = PISTO_SNE;  // export units per class (each 32 / kSNE low-resolution rows)
 #ifndef PISTO_STATIC_W3
-#define PISTO_STATIC_W3 1  // row loops with one difference field (or one scale group and two fields) keep three-tap column weights in registers (0 = select form)
+#define PISTO_STATIC_W3 2  // 1: row loops with one difference field (or one scale group and two fields) keep three-tap column weights in registers; 2: two fields too; 0 = select form
 #endif
 #ifndef PISTO_SMR
 #define PISTO_SMR 1
@@ -203,7 +203,7 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
   u64 Hb[G][K][2], Dh[G][K][2], base[K][2];
   uint32_t yb[G];  // address of the map row that holds Ha (cell of the thread's first column)
   unsigned int selm[G];
-  constexpr bool HOIST = PISTO_STATIC_W3 && (K == 1 || (G == 1 && K <= 2));  // the horizontal weights of the thread's columns stay in registers, in three-tap form (else: one 16-byte load per refill)
+  constexpr bool HOIST = PISTO_STATIC_W3 && (K == 1 || (G == 1 && K <= 2) || (PISTO_STATIC_W3 >= 2 && K <= 2));  // the horizontal weights of the thread's columns stay in registers, in three-tap form (else: one 16-byte load per refill)
   float4 L1[G] = {};
   ColWeights3 W3[HOIST ? G : 1];
   auto l1_of = [&](int gi) { return lds_f4(col4_t + gi * 16u * kSGX); };
