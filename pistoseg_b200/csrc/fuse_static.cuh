@@ -111,7 +111,7 @@ struct StaticGeom {
   int vbase[PISTO_MAX_VIEWS], vcol[PISTO_MAX_VIEWS];  // byte address of de-augmented (i, j) inside a plane: vbase + 4 w i + j vcol
   int buf_floats;
   float tau_coef, tau_abs;
-  int ctl_off, col4_off, col4i_off, lowtab_off, ymap_off, queue_off, lab_off, views_off, smem_bytes;
+  int ctl_off, col4_off, col4i_off, w3_off, lowtab_off, ymap_off, queue_off, lab_off, views_off, smem_bytes;  // w3_off: [G][56] ColWeights3 (48 B) or -1
   int* counter;
   unsigned long long* stats;          // [4] device counters of the handle (pisto_filter_stats) or NULL
 };
@@ -165,6 +165,14 @@ __device__ __forceinline__ ColWeights3 static_weights3(const float4 L1, unsigned
   w.c[0] = pack2(wc[0], wc[1]); w.c[1] = pack2(wc[2], wc[3]);
   return w;
 }
+__device__ __forceinline__ ColWeights3 static_weights3_lds(uint32_t a) {  // one table entry: three 16-byte loads
+  const int4 x = lds_i4(a), y = lds_i4(a + 16u), z = lds_i4(a + 32u);
+  ColWeights3 w;
+  w.a[0] = ((u64)(unsigned)x.y << 32) | (unsigned)x.x; w.a[1] = ((u64)(unsigned)x.w << 32) | (unsigned)x.z;
+  w.b[0] = ((u64)(unsigned)y.y << 32) | (unsigned)y.x; w.b[1] = ((u64)(unsigned)y.w << 32) | (unsigned)y.z;
+  w.c[0] = ((u64)(unsigned)z.y << 32) | (unsigned)z.x; w.c[1] = ((u64)(unsigned)z.w << 32) | (unsigned)z.z;
+  return w;
+}
 template <int K, int OFF>
 __device__ __forceinline__ void static_load_h3(uint32_t a, const ColWeights3& w, u64 (&H)[K][2]) {
   float y0[K], y1[K], y2[K];
@@ -194,9 +202,12 @@ __device__ __forceinline__ void static_load_h3(uint32_t a, const ColWeights3& w,
 // (bytes-per-float * j0 | sel << 16) word (group stride 4 * 56); lab_a: label-tile address of (first row of the strip, x)
 // Returns the rows of the strip (bit r) on which the thread's 4-pixel group failed the lead test.  PACK: the label tile holds 2 bits
 // per pixel (one byte per thread and row, row stride 56) instead of bytes.
+// w3_t != 0: address of the thread's ColWeights3 entry of group 0 in the shared-memory table (group stride 48 * 56): loops that cannot
+// keep the three-tap weights in registers (three difference fields) load them per refill -- three 16-byte loads instead of the
+// select form's 16-byte load + six selects per field + predicate set-ups.
 template <int G, int K, int U, bool PACK = false>
 __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_t col4_t, uint32_t col4i_t, uint32_t ymap_s, uint32_t lab_a, int strip,
-                                                    const unsigned int (&c4)[4], float tau) {
+                                                    const unsigned int (&c4)[4], float tau, uint32_t w3_t = 0u) {
   constexpr int KP = K == 3 ? 4 : K;
   constexpr int NBLK = kSR / U;
   static_assert(U == 32 || U == 16 || U == 8 || U == 4, "row-loop unroll: 4, 8, 16 or 32");
@@ -219,6 +230,10 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
       W3[gi] = static_weights3(L1[gi], selm[gi]);
       static_load_h3<K, 0>(yb[gi], W3[gi], Ha);
       static_load_h3<K, RS>(yb[gi], W3[gi], Hb[gi]);
+    } else if (w3_t) {
+      const ColWeights3 w = static_weights3_lds(w3_t + gi * 48u * kSGX);
+      static_load_h3<K, 0>(yb[gi], w, Ha);
+      static_load_h3<K, RS>(yb[gi], w, Hb[gi]);
     } else {
       static_load_h<K, 0>(yb[gi], L1[gi], selm[gi], Ha);
       static_load_h<K, RS>(yb[gi], L1[gi], selm[gi], Hb[gi]);
@@ -262,6 +277,7 @@ __device__ __forceinline__ unsigned int static_rows(const StaticGeom& g, uint32_
             yb[gi] += RS;
             u64 Hn[K][2];
             if constexpr (HOIST) static_load_h3<K, RS>(yb[gi], W3[gi], Hn);
+            else if (w3_t) static_load_h3<K, RS>(yb[gi], static_weights3_lds(w3_t + gi * 48u * kSGX), Hn);
             else static_load_h<K, RS>(yb[gi], l1_of(gi), selm[gi], Hn);
 #pragma unroll
             for (int k = 0; k < K; k++)
@@ -741,6 +757,11 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
 #pragma unroll
     for (int c = 1; c < 2 * NP; c++) sel |= (unsigned)(L[c].i0 - L[0].i0) << c;  // 0 or 1 (checked on the host)
     col4i[i] = (unsigned)(4 * L[0].i0) | (sel << 16);
+    if (NP == 2 && g.w3_off >= 0) {
+      const ColWeights3 w = static_weights3(make_float4(L[0].l1, L[1].l1, L[2 * NP - 2].l1, L[2 * NP - 1].l1), sel);
+      u64* dst = reinterpret_cast<u64*>(smem_raw + g.w3_off) + 6 * i;
+      dst[0] = w.a[0]; dst[1] = w.a[1]; dst[2] = w.b[0]; dst[3] = w.b[1]; dst[4] = w.c[0]; dst[5] = w.c[1];
+    }
   }
 
   if (need_low && tid < 32) {
@@ -847,6 +868,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
   const int x = 2 * NP * grp;
   const uint32_t ymap_s = smem_u32(ymap);
   const uint32_t col4_t = smem_u32(col4) + 8u * NP * grp, col4i_t = smem_u32(col4i) + 4u * grp;
+  const uint32_t w3_t = (NP == 2 && g.w3_off >= 0) ? smem_u32(smem_raw + g.w3_off) + 48u * grp : 0u;
   const uint32_t lab_s = smem_u32(labsm);
   const int nt = ncomp;
   constexpr long long tpx = (long long)kST * kST;
@@ -983,7 +1005,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         if constexpr (NP == 2) {
           if (P == 2) unc = static_rows<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
           else if (P == 3) unc = static_rows<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
-          else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
+          else if (C >= 4 && P == 4) unc = static_rows<G, (C >= 4 ? 3 : 1), kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau, w3_t);
         } else {
           if (P == 2) unc = static_rows1<G, 1, kSU1>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
           else if (P == 3) unc = static_rows1<G, 2, kSU2>(g, col4_t, col4i_t, ymap_s, lab_a, strip, c4, tau);
@@ -1652,6 +1674,8 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   g->ctl_off = off; off += (int)((sizeof(FCtl) + 127) & ~127u);
   g->col4_off = off; off += 16 * G * kSGX;                        // [G][56] float4, or [G][112] float2
   g->col4i_off = off; off += 4 * G * 2 * kSGX; off = (off + 15) & ~15;
+  g->w3_off = -1;
+  if (C >= 4 && np == 2) { g->w3_off = off; off += 48 * G * kSGX; }   // only the three-field loop reads it
   g->lowtab_off = off; off += low ? 32 * (8 * V + 8 * G) : 0;
   g->ymap_off = off; off += st_ybytes(G, G, KPmax);
   g->queue_off = off; off += 4 * kFQueueCap;
