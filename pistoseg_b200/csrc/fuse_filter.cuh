@@ -90,6 +90,13 @@ struct FCtl {
   // producer lane: {presence bits, single label or -1, candidate classes (one byte each, ascending), staging shifts of the
   // views ((address & 12) >> 2, two bits per view) | number of candidates << 28}
   uint4 head[2];
+  // fuse_static.cuh, deferred exact pass: group queues in eight rotating slots (tile k of the CTA uses slot k & 7; a dedicated warp
+  // empties it once every compute warp has counted the tile done), the tile each slot belongs to, and the hand-shake counters
+  unsigned int qn[8];
+  int2 qmeta[8];            // {tile index, presence bits}
+  unsigned int tiles_done;  // += 1 per compute warp and tile (after its last store of the tile)
+  unsigned int fixed;       // tiles whose queue has been emptied
+  int ntiles;               // number of tiles this CTA processed, -1 until the producer knows
 };
 
 // label among cls[0..K] from the difference candidates (0, d[0] .. d[K-1]); returns whether the lead exceeds tau

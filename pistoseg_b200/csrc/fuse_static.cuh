@@ -92,6 +92,9 @@ constexpr int kSU2 = PISTO_SU2;  // ... for two / three fields (code size: the i
 #endif
 constexpr int kSAux = PISTO_SAUX;  // warps that only work on the 32x32 export
 constexpr int kSNE = PISTO_SNE;  // export units per class (each 32 / kSNE low-resolution rows)
+#ifndef PISTO_STATIC_DEFER
+#define PISTO_STATIC_DEFER 1  // uncertain pixels are re-evaluated by the producer warp after the tile (0: recheck + exact pass inside the tile)
+#endif
 #ifndef PISTO_STATIC_W3
 #define PISTO_STATIC_W3 2  // 1: row loops with one difference field (or one scale group and two fields) keep three-tap column weights in registers; 2: two fields too; 0 = select form
 #endif
@@ -742,6 +745,8 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     ctl->maxbits[0] = ctl->maxbits[1] = 0u;
     ctl->lownext[0] = ctl->lownext[1] = 0u;
     ctl->qcount[0] = ctl->qcount[1] = 0u;
+    for (int i = 0; i < 8; i++) ctl->qn[i] = 0u;
+    ctl->tiles_done = 0u; ctl->fixed = 0u; ctl->ntiles = -1;
   }
   for (int i = tid; i < 64; i += nthreads) ctl->hist[i] = 0;
   for (int i = tid; i < G * GX; i += nthreads) {
@@ -800,6 +805,85 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
   __syncthreads();
 
   const int ncomp = g.cwarps * 32;
+  // Deferred exact pass (4 columns per thread): a row whose 4-pixel group fails the lead test is NOT re-evaluated by the compute warps.
+  // The thread pushes (row, first column, the 4 labels it stored) to the tile's queue and goes on; the vector pass writes those labels
+  // like any other.  A dedicated FIXER warp -- the CTA has two warp slots to spare -- waits until every compute warp has counted the
+  // tile done, evaluates the queued pixels exactly from global memory (the tile's views were streamed microseconds ago: L2), one pixel
+  // per lane, operation by operation as torch does, and patches the few labels that differ (respecting the background overwrite;
+  // confusion counts through global atomics).  What this takes off the compute warps' critical path: the in-thread recheck (150-400
+  // dependent instructions in ONE thread before the barrier), the CTA-wide exact pass and the barrier after it -- a build that never
+  // flags measured +8 % on cfg 2 and +11 % on cfg 3.  Queues rotate through 8 slots of 128 groups; an overflowing queue (adversarial
+  // inputs) makes the compute warps evaluate the whole tile exactly inside the tile, as before.
+  constexpr bool DEFER = PISTO_STATIC_DEFER && NP == 2;
+  constexpr int kQS = 8, kGQ = kFQueueCap / (2 * kQS);  // slots; queued groups per slot: entries[kGQ] + labels[kGQ]
+  if (DEFER && tid >= ncomp + 32 * g.aux + 32) {
+    // ===== fixer warp
+    const int lane = tid & 31;
+    const long long tile_px = (long long)kST * kST;
+    volatile unsigned int* v_done = &ctl->tiles_done;
+    volatile int* v_ntiles = &ctl->ntiles;
+    for (int kk = 0;; kk++) {
+      for (int it = 0;; it++) {  // wait for tile kk of this CTA to be complete, or for the end of the tile stream
+        if (*v_done >= (unsigned)(kk + 1) * (unsigned)g.cwarps) break;
+        const int nt_ = *v_ntiles;
+        if (nt_ >= 0 && kk >= nt_) return;
+        __nanosleep(it < 4 ? 100 : 400);
+      }
+      __threadfence_block();  // the tile's label stores (other warps) are ordered before the patches below
+      const int s = kk & (kQS - 1);
+      const unsigned int nq = ctl->qn[s];
+      if (nq) {
+        const int2 m = ctl->qmeta[s];
+        const int tile = m.x;
+        const unsigned int bits = (unsigned)m.y;
+        const uint32_t* qb = queue + s * (2 * kGQ);
+        const uint32_t* labs = qb + kGQ;
+        for (int pi = lane; pi < 4 * (int)nq; pi += 32) {
+          const uint32_t e = qb[pi >> 2];
+          const int yy = (int)(e >> 16), xx = (int)(e & 0xffffu) + (pi & 3);
+          const unsigned int old = (labs[pi >> 2] >> (8 * (pi & 3))) & 0xffu;
+          float a[C];
+#pragma unroll
+          for (int c = 0; c < C; c++) a[c] = 0.f;
+#pragma unroll 1  // (rolled: this warp runs beside the compute warps, its code must not compete for their instruction cache)
+          for (int v = 0; v < V; v++) {
+            const ViewDev& vw = p.view[v];
+            const Lerp Ly = pisto_src_index(vw.scale_h, yy, vw.map.ho, false);
+            const Lerp Lx = pisto_src_index(vw.scale_w, xx, vw.map.wo, false);
+            const int r0 = g.vbase[v] + Ly.i0 * 4 * vw.w, r1 = g.vbase[v] + Ly.i1 * 4 * vw.w;
+            const int c0 = Lx.i0 * g.vcol[v], c1 = Lx.i1 * g.vcol[v];
+            const float* gsrc = vw.logits + (long long)tile * vw.tile_stride;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+              const int pl = c * 4 * vw.h * vw.w;
+              const float x00 = __ldg(gsrc + ((r0 + pl + c0) >> 2)), x01 = __ldg(gsrc + ((r0 + pl + c1) >> 2));
+              const float x10 = __ldg(gsrc + ((r1 + pl + c0) >> 2)), x11 = __ldg(gsrc + ((r1 + pl + c1) >> 2));
+              const float h0 = __fmaf_rn(Lx.l0, x00, __fmul_rn(Lx.l1, x01));
+              const float h1 = __fmaf_rn(Lx.l0, x10, __fmul_rn(Lx.l1, x11));
+              const float u = __fmaf_rn(Ly.l0, h0, __fmul_rn(Ly.l1, h1));
+              a[c] = (v == 0) ? u : __fadd_rn(a[c], u);
+            }
+          }
+          const unsigned int lab = (unsigned)pisto_decide<C>(a, bits, p.dec, false, nullptr);
+          if (lab != old) {
+            const long long px = (long long)tile * tile_px + yy * kST + xx;
+            if (do_conf) {
+              const unsigned int gg = p.gt[px];
+              if (gg < (unsigned)C) { atomicAdd(&p.conf[gg * C + old], ~0ull); atomicAdd(&p.conf[gg * C + lab], 1ull); }
+            }
+            if (has_label && !(has_bg && p.bg[px] == (uint8_t)p.bg_match)) p.label_out[px] = (uint8_t)lab;
+          }
+        }
+        if (lane == 0 && g.stats) atomicAdd(&g.stats[2], 4ull * nq);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ctl->qn[s] = 0u;
+        __threadfence_block();
+        *reinterpret_cast<volatile unsigned int*>(&ctl->fixed) = (unsigned)(kk + 1);
+      }
+    }
+  }
   if (tid >= ncomp + 32 * g.aux) {
     // ===== producer warp
     if (tid == ncomp + 32 * g.aux) {
@@ -812,11 +896,16 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         const int b = NB == 2 ? (k & 1) : 0;
         if (k >= NB) mbar_wait_sleep(&ctl->empty[b], NB == 2 ? (((k >> 1) - 1) & 1) : ((k - 1) & 1));
         const int tile = next < p.N ? next : -1;
+        if (DEFER && tile >= 0 && k >= kQS) {  // queue slot k & 7 was last used by tile k - 8: it must have been emptied (it always has)
+          volatile unsigned int* v_fixed = &ctl->fixed;
+          while (*v_fixed + (unsigned)kQS < (unsigned)k + 1u) __nanosleep(200);
+        }
         ctl->tile[b] = tile;
         ctl->pres_bits[b] = next_tp.bits;
         ctl->pres_single[b] = next_tp.single;
         ctl->lownext[b] = 0u;
         if (tile >= 0) ctl->head[b] = static_tile_head<C, V>(p, tile, next_tp);
+        if (tile < 0 && DEFER) { *reinterpret_cast<volatile int*>(&ctl->ntiles) = k; }
         if (tile >= 0 && next_views) issue_tile(tile, b);
         else mbar_arrive(&ctl->full[b]);
         if (tile < 0) break;
@@ -878,6 +967,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
   for (int k = 0;; k++) {
     const int b = k & 1;
     const int sb = NB == 2 ? b : 0;
+    const int qs = k & (kQS - 1);  // queue slot of the deferred exact pass
     mbar_wait(&ctl->full[sb], NB == 2 ? ((k >> 1) & 1) : (k & 1));
     const int n = ctl->tile[sb];
     if (n < 0) break;
@@ -897,6 +987,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
 #pragma unroll
     for (int c = 0; c < C; c++) cls[c] = (int)(((unsigned)hd.z >> (8 * c)) & 0xffu);
     const int P = (int)((unsigned)hd.w >> 28);
+    if (DEFER && tid == 0) ctl->qmeta[qs] = make_int2(n, (int)tp.bits);  // whose queue slot qs is (read by the fixer warp after the tile)
 
 #ifdef PISTO_X_SKIP_PREPASS
     if (false) {
@@ -919,7 +1010,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
     }
     phase_sync(0);  // difference maps + max visible; every thread has left the previous tile
     if (NB == 1 && (tid & 31) == 0) mbar_arrive(&ctl->empty[0]);
-    if (tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone
+    if (!DEFER && tid == 0) ctl->qcount[b ^ 1] = 0u;  // the previous tile's queue has been read by everyone
 
     // The byte masks of the vector pass' first batch are requested as soon as the registers are free -- right away for single-label
     // tiles, after the row loop otherwise -- so that their latency is covered by the barrier and the exact pass.
@@ -1013,30 +1104,46 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
         }
       }
       if (unc) {
-        // (Measured and dropped: pushing the 4 pixels of a flagged row straight to the queue, without the in-thread recheck: -5 %.
-        // The recheck clears three of four pixels and overlaps with the other warps' rows; the exact pass runs between two barriers.)
-        if (P == 2) static_push_rows<G, 1, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
-        else if (P == 3) static_push_rows<G, 2, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
-        else static_push_rows<G, (C >= 4 ? 3 : 1), NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+        if constexpr (DEFER) {
+          // flagged rows -> (row, first column) + the 4 labels the thread stored for that row; the producer warp takes it from there
+          const uint32_t lab_a = lab_s + (uint32_t)(strip * kSR * kST + x);
+          unsigned int idx = atomicAdd(&ctl->qn[qs], (unsigned)__popc(unc));
+          while (unc) {
+            const int r = __ffs(unc) - 1;
+            unc &= unc - 1;
+            if (idx < (unsigned)kGQ) {
+              queue[qs * (2 * kGQ) + idx] = ((unsigned)(strip * kSR + r) << 16) | (unsigned)x;
+              queue[qs * (2 * kGQ) + kGQ + idx] = lds_u32(lab_a + (uint32_t)(r * kST));
+            }
+            idx++;
+          }
+        } else {
+          // in-tile variant: the thread re-evaluates a flagged row per pixel and queues only the pixels that still fail
+          if (P == 2) static_push_rows<G, 1, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+          else if (P == 3) static_push_rows<G, 2, NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+          else static_push_rows<G, (C >= 4 ? 3 : 1), NP>(ctl, queue, kFQueueCap, b, col4_t, col4i_t, ymap_s, strip * kSR, x, unc, tau);
+        }
       }
       request_masks();
       phase_sync(1);  // every strip done: the queue is complete; everyone has read maxbits
       if (tid == 0) ctl->maxbits[b] = 0u;
-      // Pixels that failed the lead test (about 1e-4 of them on Gaussian logits) are re-evaluated exactly -- operation by
-      // operation as torch does -- one pixel per warp at a time, spread over all warps.
-      const unsigned int nq = ctl->qcount[b];
+      const unsigned int nq = DEFER ? ctl->qn[qs] : ctl->qcount[b];
       if (tid == 0 && g.stats) {  // data-dependence record: queued pixels, whole-tile fallbacks (pisto_filter_stats)
         atomicAdd(&g.stats[1], 1ull);
-        if (!exact_all && nq <= (unsigned)kFQueueCap) atomicAdd(&g.stats[2], (unsigned long long)nq); else atomicAdd(&g.stats[3], 1ull);
+        if (!exact_all && nq <= (unsigned)(DEFER ? kGQ : kFQueueCap)) { if (!DEFER) atomicAdd(&g.stats[2], (unsigned long long)nq); } else atomicAdd(&g.stats[3], 1ull);
       }
-      if (nq > (unsigned)kFQueueCap) exact_all = true;  // overflow: redo the whole tile
-      if (!exact_all && nq) {
-        for (int j = tid >> 5; j < (int)nq; j += g.cwarps) {
-          const uint32_t e = queue[j];
-          exact_warp((int)(e >> 16), (int)(e & 0xffffu));
+      if (nq > (unsigned)(DEFER ? kGQ : kFQueueCap)) exact_all = true;  // overflow: redo the whole tile
+      if constexpr (!DEFER) {
+        // Pixels that failed the lead test are re-evaluated exactly -- operation by operation as torch does -- one pixel per warp at a
+        // time, spread over all warps.
+        if (!exact_all && nq) {
+          for (int j = tid >> 5; j < (int)nq; j += g.cwarps) {
+            const uint32_t e = queue[j];
+            exact_warp((int)(e >> 16), (int)(e & 0xffffu));
+          }
         }
+        if (!exact_all && nq) phase_sync(2);  // label tile complete
       }
-      if (!exact_all && nq) phase_sync(2);  // label tile complete
       if (exact_all) {  // non-finite / absurd magnitudes, empty presence vector: the whole tile follows the reference pixel by pixel
         for (int j = tid; j < kST * kST; j += nt) {
           const int yy = j / kST, xx = j - yy * kST;
@@ -1069,6 +1176,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
           labsm[j] = (uint8_t)pisto_decide<C>(a, tp.bits, p.dec, false, nullptr);
         }
         phase_sync(2);
+        if (DEFER && tid == 0) ctl->qn[qs] = 0u;  // the tile is exact as a whole: nothing left for the deferred pass
       }
     }
 
@@ -1153,6 +1261,7 @@ __device__ __forceinline__ void fuse_static_body(const FuseParams& p, const Stat
 #endif
     __syncwarp();
     if (NB == 2 && (tid & 31) == 0) mbar_arrive(&ctl->empty[sb]);
+    if (DEFER && !is_export && (tid & 31) == 0) { __threadfence_block(); atomicAdd(&ctl->tiles_done, 1u); }  // this warp's stores of the tile are out
   }
   if (do_conf) {
     bar_sync(1, ncomp);
@@ -1659,7 +1768,7 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
     }
   g->aux = low ? kSAux : 0;
   g->cwarps = (kST / (2 * np) * kSS + 31) / 32;
-  g->threads = g->cwarps * 32 + 32 * g->aux + 32;
+  g->threads = g->cwarps * 32 + 32 * g->aux + 32 + ((PISTO_STATIC_DEFER && np == 2) ? 32 : 0);  // + producer warp (+ fixer warp)
   int fl = 0;
   for (int v = 0; v < V; v++) {
     g->view_off[v] = fl;
@@ -1678,7 +1787,7 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   if (C >= 4 && np == 2) { g->w3_off = off; off += 48 * G * kSGX; }   // only the three-field loop reads it
   g->lowtab_off = off; off += low ? 32 * (8 * V + 8 * G) : 0;
   g->ymap_off = off; off += st_ybytes(G, G, KPmax);
-  g->queue_off = off; off += 4 * kFQueueCap;
+  g->queue_off = off; off += 4 * kFQueueCap;  // in-tile queue, or 8 slots x (64 entries + 64 label words) of the deferred exact pass
   g->lab_off = off; off += kST * kST;
   off = (off + 127) & ~127;
   g->views_off = off; off += nbuf * 4 * fl + 256;  // slack: the export's shared row loads may touch one row past the last view
