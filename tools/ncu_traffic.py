@@ -17,7 +17,7 @@ res = {
     "mufu_pipe_frac": get("sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active") / 100,
     "dram_throughput_frac_under_ncu": get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") / 100,
     "warps_per_sm": get("sm__warps_active.avg.pct_of_peak_sustained_active") / 100 * 64,
-    "binding": "instruction issue / dependent-instruction latency at 14 warps per SM (128 registers x 448 threads, 202 KB shared memory: one CTA); see DESIGN.md 4.1",
+    "binding": "instruction issue / dependent-instruction latency at 15 warps per SM (13 compute + producer + fixer; 128 registers x 480 threads, 202 KB shared memory: one CTA); see DESIGN.md 4.1",
     "source": note,
 }
 tj = {"kernel": vals[hdr.index("Kernel Name")], "tiles_per_launch": tiles, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
