@@ -77,7 +77,7 @@ int pisto_destroy(pisto_handle_t h);
 /* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t pisto_launch_count(pisto_handle_t h);
 /* Data-dependence record of the filtered fusion kernels (the label fast path trusts a pixel only above an error-bound margin and
- * re-evaluates the others exactly): out_host[1] = multi-label tiles processed, out_host[2] = pixels that went through the exact
+ * re-evaluates the others exactly -- in whole 4-pixel groups, by the shape-specialised kernel's fixer warp): out_host[1] = multi-label tiles processed, out_host[2] = pixels that went through the exact
  * pass, out_host[3] = tiles evaluated exactly as a whole (queue overflow, non-finite / absurd logits, empty presence vector);
  * out_host[0] = mosaic cells still rejected by the "background < 80 %" test at the last of max_tries draws (pisto_mosaic_plan_cells
  * accepts them -- the reference would loop for ever -- but never silently).  Synchronises the device; reset != 0 zeroes the counters afterwards. */
