@@ -128,6 +128,10 @@ typedef struct {
   float* entropy_out;     /* [N][T_h][T_w] or NULL */
   float* lowres_out;      /* [N][C][low_h][low_w] or NULL */
   unsigned long long* conf; /* [C*C] accumulated, or NULL */
+  uint8_t* label_raw_out;   /* [N][T_h][T_w] or NULL: the labels of the same scores decided with PISTO_DECIDE_RAW (argmax of the fused logits),
+                             * written beside label_out in the same pass, with the same background overwrite.  segmentation_test.py:137-139,182
+                             * needs both for BCSS -- softmax-argmax for the confusion matrix, logit-argmax for the PNG -- and read the logits
+                             * twice.  Served by the one-view full-resolution kernel and the generic kernel (impl 0 / 1). */
 } pisto_fuse_args_t;
 
 int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t* views_host, int V, const pisto_fuse_args_t* args_host,

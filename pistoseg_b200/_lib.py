@@ -36,7 +36,7 @@ class FuseArgs(C.Structure):
                 ("impl", C.c_int32),
                 ("present", C.c_void_p), ("bg", C.c_void_p), ("gt", C.c_void_p), ("label_out", C.c_void_p),
                 ("fused_out", C.c_void_p), ("entropy_out", C.c_void_p), ("lowres_out", C.c_void_p),
-                ("conf", C.c_void_p)]
+                ("conf", C.c_void_p), ("label_raw_out", C.c_void_p)]
 
 
 class TilePos(C.Structure):

@@ -30,7 +30,7 @@ int pisto_build_fuse_params(const pisto_view_t* views, int V, const pisto_fuse_a
   p.dec.rcp_v = 1.0f / (float)V;
   p.bg_match = a->bg_match; p.bg_label = a->bg_label;
   p.present = a->present; p.bg = a->bg; p.gt = a->gt;
-  p.label_out = a->label_out; p.fused_out = a->fused_out; p.entropy_out = a->entropy_out; p.lowres_out = a->lowres_out;
+  p.label_out = a->label_out; p.label_raw_out = a->label_raw_out; p.fused_out = a->fused_out; p.entropy_out = a->entropy_out; p.lowres_out = a->lowres_out;
   p.conf = a->conf;
   for (int v = 0; v < V; v++) {
     const pisto_view_t& s = views[v];
@@ -75,15 +75,20 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
   cudaStream_t st = (cudaStream_t)stream;
   PISTO_CUDA(cudaSetDevice(h->device));
   bool launched = false;
+  const bool raw2 = p.label_raw_out != nullptr;  // second label output: the one-view kernel or the generic kernel
+  if (raw2 && a->impl > 1) {
+    pisto_set_error("pisto_fuse_argmax_confusion: label_raw_out is served by impl 0 / 1 only (asked for impl=%d)", a->impl);
+    return PISTO_ERR_UNSUPPORTED;
+  }
   if (a->impl == 0) {  // one full-resolution view: pure streaming kernel
     rc = pisto_launch_fuse_identity(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
   }
-  if (!launched && a->impl == 0) {  // several full-resolution views (ttach d4 on full-resolution logits)
+  if (!launched && !raw2 && a->impl == 0) {  // several full-resolution views (ttach d4 on full-resolution logits)
     rc = pisto_launch_fuse_fullres(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
   }
-  if (!launched && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6 || a->impl == 7 || a->impl == 8)) {
+  if (!launched && !raw2 && (a->impl == 0 || a->impl == 3 || a->impl == 4 || a->impl == 6 || a->impl == 7 || a->impl == 8)) {
     rc = pisto_launch_fuse_filter(h, p, st, a->impl == 0 ? 0 : (a->impl >= 6 ? a->impl - 3 : a->impl - 2), &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched && a->impl != 0) {
@@ -92,7 +97,7 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
       return PISTO_ERR_UNSUPPORTED;
     }
   }
-  if (!launched && (a->impl == 0 || a->impl == 5)) {  // large tiles: the same filter on output blocks
+  if (!launched && !raw2 && (a->impl == 0 || a->impl == 5)) {  // large tiles: the same filter on output blocks
     rc = pisto_launch_fuse_band(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched && a->impl == 5) {
@@ -101,7 +106,7 @@ extern "C" int pisto_fuse_argmax_confusion(pisto_handle_t h, const pisto_view_t*
       return PISTO_ERR_UNSUPPORTED;
     }
   }
-  if (!launched && a->impl != 1) {
+  if (!launched && !raw2 && a->impl != 1) {
     rc = pisto_launch_fuse_stream(h, p, st, &launched);
     if (rc != PISTO_OK) return rc;
     if (!launched) {

@@ -22,6 +22,7 @@ struct FuseParams {
   const uint8_t* bg;
   const uint8_t* gt;
   uint8_t* label_out;
+  uint8_t* label_raw_out;  // second label output, decided with PISTO_DECIDE_RAW (identity / generic kernels only)
   float* fused_out;
   float* entropy_out;
   float* lowres_out;

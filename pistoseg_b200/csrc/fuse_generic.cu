@@ -66,6 +66,16 @@ __global__ void __launch_bounds__(kThreads) fuse_generic_kernel(const __grid_con
       if (p.bg && p.bg[idx] == (uint8_t)p.bg_match) out = p.bg_label;
       p.label_out[idx] = (uint8_t)out;
     }
+    if (p.label_raw_out) {
+      int out = tp.single;
+      if (tp.single < 0) {
+        DecideCfg raw = p.dec;
+        raw.decide_mode = PISTO_DECIDE_RAW;
+        out = pisto_decide<C>(a, tp.bits, raw, false, nullptr);
+      }
+      if (p.bg && p.bg[idx] == (uint8_t)p.bg_match) out = p.bg_label;
+      p.label_raw_out[idx] = (uint8_t)out;
+    }
   }
   if (do_conf) {
     __syncthreads();

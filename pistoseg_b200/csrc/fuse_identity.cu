@@ -90,16 +90,17 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         for (int c = 0; c < C; c++) gr.v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
       }
       if (do_conf) gr.g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
-      if (p.label_out && p.bg) gr.bg4 = __ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix));
+      if ((p.label_out || p.label_raw_out) && p.bg) gr.bg4 = __ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix));
     }
     return gr;
   };
   auto process = [&](const Group& gr) {
     if (!gr.live) return;
     const TilePresence tp = gr.tp;
-    int lab[4];
+    int lab[4], labr[4];
     if (!gr.scores) {
       lab[0] = lab[1] = lab[2] = lab[3] = tp.single;
+      labr[0] = labr[1] = labr[2] = labr[3] = tp.single;
     } else {
       float a[4][C];
 #pragma unroll
@@ -110,10 +111,18 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         for (int j = 0; j < 4; j++) lab[j] = identity_decide_fast<C>(a[j], p.dec);
         all_ok = (lab[0] | lab[1] | lab[2] | lab[3]) >= 0;
       }
+      // second output (PISTO_DECIDE_RAW): where the cheap decision held, the leader's margin makes argmax(softmax) == argmax(logits)
+#pragma unroll
+      for (int j = 0; j < 4; j++) labr[j] = lab[j];
       if (!all_ok) {
+        DecideCfg raw = p.dec;
+        raw.decide_mode = PISTO_DECIDE_RAW;
 #pragma unroll
         for (int j = 0; j < 4; j++)
-          if (!unmasked || lab[j] < 0) lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
+          if (!unmasked || lab[j] < 0) {
+            lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
+            if (p.label_raw_out) labr[j] = pisto_decide<C>(a[j], tp.bits, raw, false, nullptr);
+          }
       }
     }
     const long long pix = (long long)gr.n * hw + gr.r4;
@@ -125,6 +134,14 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
       }
       *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
+    }
+    if (p.label_raw_out) {
+      unsigned int o = (unsigned)labr[0] | ((unsigned)labr[1] << 8) | ((unsigned)labr[2] << 16) | ((unsigned)labr[3] << 24);
+      if (p.bg) {
+        const unsigned int eq = __vcmpeq4(gr.bg4, 0x01010101u * (unsigned)p.bg_match);
+        o = ((0x01010101u * (unsigned)p.bg_label) & eq) | (o & ~eq);
+      }
+      *reinterpret_cast<unsigned int*>(p.label_raw_out + pix) = o;
     }
     if (do_conf) {
 #pragma unroll
@@ -173,7 +190,7 @@ int pisto_launch_fuse_identity(pisto_ctx* h, const FuseParams& p, cudaStream_t s
   if (!(vw.same_h && vw.same_w && m.a0 == 0 && m.ai == 1 && m.aj == 0 && m.b0 == 0 && m.bi == 0 && m.bj == 1)) return PISTO_OK;
   const long long hw = (long long)p.T_h * p.T_w;
   if (hw % 4 || vw.tile_stride % 4) return PISTO_OK;
-  if (((uintptr_t)vw.logits & 15) || (((uintptr_t)p.label_out | (uintptr_t)p.bg | (uintptr_t)p.gt) & 3)) return PISTO_OK;
+  if (((uintptr_t)vw.logits & 15) || (((uintptr_t)p.label_out | (uintptr_t)p.label_raw_out | (uintptr_t)p.bg | (uintptr_t)p.gt) & 3)) return PISTO_OK;
   const long long total = hw / 4 * p.N;
   long long grid = (total + kThreads - 1) / kThreads;
   const long long cap = (long long)h->sm_count * 16;

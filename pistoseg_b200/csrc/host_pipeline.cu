@@ -65,6 +65,7 @@ extern "C" int pisto_fuse_argmax_confusion_host(pisto_handle_t h, const pisto_vi
     view_off[v] = off;
     if (!view_on_device[v]) off = align_up(off + view_tile_bytes[v] * chunk, 256);
   }
+  PISTO_REQUIRE(!a->label_raw_out, "pisto_fuse_argmax_confusion_host: label_raw_out is not supported by the host-buffer variant");
   size_t o_present = off; if (a->present) off = align_up(off + (size_t)chunk * C, 256);
   size_t o_bg = off; if (a->bg) off = align_up(off + px * chunk, 256);
   size_t o_gt = off; if (a->gt) off = align_up(off + px * chunk, 256);

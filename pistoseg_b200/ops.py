@@ -85,7 +85,7 @@ def _make_views(views, xforms, C_):
 
 def fuse_argmax_confusion(views, xforms=None, size=None, *, fuse_mode=FUSE_LOGIT_MEAN, mask_mode=MASK_NONE,
                           decide=DECIDE_SOFTMAX, present=None, bg=None, bg_match=0, bg_label=None, gt=None, conf=None,
-                          want_labels=True, want_fused=False, want_entropy=False, lowres=None, impl=IMPL_AUTO):
+                          want_labels=True, want_fused=False, want_entropy=False, lowres=None, impl=IMPL_AUTO, want_raw_labels=False):
     """The fused hot path (include/pistoseg_b200.h: pisto_fuse_argmax_confusion).
 
     views   list of CUDA float32 [N,C,h_v,w_v] logits as the backbone produced them for each augmented input
@@ -93,6 +93,8 @@ def fuse_argmax_confusion(views, xforms=None, size=None, *, fuse_mode=FUSE_LOGIT
     size    (T_h, T_w) output tile size, default = de-augmented size of view 0
     Returns a dict with the requested outputs: labels u8 [N,T_h,T_w], fused f32 [N,C,T_h,T_w],
     entropy f32 [N,T_h,T_w], lowres f32 [N,C,lh,lw], conf (the int64 [C,C] tensor passed in, updated in place).
+    want_raw_labels: also ``labels_raw`` u8 [N,T_h,T_w] = the same scores decided with DECIDE_RAW, written in the same pass
+    (one full-resolution view or impl=IMPL_GENERIC; segmentation_test.py:137-139,182).
     """
     v0 = views[0]
     dev = _dev_index(v0)
@@ -122,6 +124,9 @@ def fuse_argmax_confusion(views, xforms=None, size=None, *, fuse_mode=FUSE_LOGIT
     if want_labels:
         out["labels"] = torch.empty((N, T_h, T_w), dtype=torch.uint8, device=device)
         a.label_out = out["labels"].data_ptr()
+    if want_raw_labels:
+        out["labels_raw"] = torch.empty((N, T_h, T_w), dtype=torch.uint8, device=device)
+        a.label_raw_out = out["labels_raw"].data_ptr()
     if want_fused or (lowres is not None and not _is_gather((T_h, T_w), lowres)):
         out["fused"] = torch.empty((N, C_, T_h, T_w), dtype=torch.float32, device=device)
         a.fused_out = out["fused"].data_ptr()

@@ -146,9 +146,10 @@ def main(args, model=None, dataset=None, image_size=None, load_gt=None):
                     sel = torch.tensor([t[0] for t in items], device=device)
                     fusers[idx].add_tiles(output.index_select(0, sel), scale, [t[1] for t in items], [t[2] for t in items])
             else:
+                # one pass over the logits: softmax-argmax into the confusion matrix (:137-139) and logit-argmax for the PNG (:182)
                 out = ops.fuse_argmax_confusion([output], [0], output.shape[-2:], decide=_lib.DECIDE_SOFTMAX, gt=mask_batch.to(device).byte(),
-                                                conf=test_iou._acc(device))
-                raw = ops.fuse_argmax_confusion([output], [0], output.shape[-2:], decide=_lib.DECIDE_RAW)["labels"].cpu().numpy()  # :182 argmax of logits
+                                                conf=test_iou._acc(device), want_labels=False, want_raw_labels=True)
+                raw = out["labels_raw"].cpu().numpy()
                 for j, name in enumerate(name_batch):
                     writer.submit(pio.save_mask_png, raw[j], os.path.join(args.save_dir, "mask", name), palette)
                 del out

@@ -265,3 +265,37 @@ def test_fullres_d4_kernel_equals_generic_and_oracle(cuda, T, C):
     kw.update(want_fused=False, lowres=None)
     a2 = ops.fuse_argmax_confusion(vg, codes, T, conf=ops.new_confusion(C, cuda), **kw)
     assert torch.equal(a2["labels"], b["labels"]) and torch.equal(a2["conf"], b["conf"])
+
+
+@pytest.mark.parametrize("C", [3, 4])
+def test_second_label_output_equals_a_separate_raw_pass(cuda, C):
+    """label_raw_out (segmentation_test.py:137-139,182: softmax-argmax for the matrix, logit-argmax for the PNG, one pass over the logits):
+    labels == the DECIDE_SOFTMAX call's, labels_raw == the DECIDE_RAW call's, the confusion matrix is the softmax one -- on the one-view
+    full-resolution kernel and on the generic kernel, with near ties, exact ties, a presence vector and a background mask."""
+    from pistoseg_b200 import _lib
+    g = torch.Generator().manual_seed(70 + C)
+    N, T = 6, 224
+    x = torch.randn((N, C, T, T), generator=g) * 2
+    x[1, 1] = x[1, 0] + torch.randn((T, T), generator=g) * 1e-7          # near ties
+    x[2] = torch.round(x[2])                                                # exact ties
+    x[3, :, 5, 7] = float("nan")
+    gt = torch.randint(0, C + 1, (N, T, T), generator=g, dtype=torch.uint8)
+    bg = (torch.rand((N, T, T), generator=g) < 0.1).to(torch.uint8)
+    present = synthetic.make_present(N, C, 9, single_frac=0.3)
+    for impl in (0, IMPL_GENERIC):
+        for kw in (dict(), dict(present=present.to(cuda), mask_mode=MASK_FILL, bg=bg.to(cuda), bg_match=1, bg_label=C)):
+            conf2 = ops.new_confusion(C, cuda)
+            both = ops.fuse_argmax_confusion([x.to(cuda)], [0], (T, T), decide=DECIDE_SOFTMAX, gt=gt.to(cuda), conf=conf2, impl=impl,
+                                             want_raw_labels=True, **kw)
+            conf1 = ops.new_confusion(C, cuda)
+            soft = ops.fuse_argmax_confusion([x.to(cuda)], [0], (T, T), decide=DECIDE_SOFTMAX, gt=gt.to(cuda), conf=conf1, impl=impl, **kw)
+            raw = ops.fuse_argmax_confusion([x.to(cuda)], [0], (T, T), decide=DECIDE_RAW, impl=impl, **kw)
+            assert torch.equal(both["labels"], soft["labels"]) and torch.equal(conf2, conf1)
+            assert torch.equal(both["labels_raw"], raw["labels"])
+    # several views: only the generic kernel serves the second output; a forced fast kernel refuses
+    cfg = synthetic.cfg2(N=4)
+    views = [v.to(cuda) for v in cfg["views"]]
+    both = ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), decide=DECIDE_SOFTMAX, want_raw_labels=True)
+    assert torch.equal(both["labels_raw"], ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), decide=DECIDE_RAW, impl=IMPL_GENERIC)["labels"])
+    with pytest.raises(_lib.PistoError):
+        ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), decide=DECIDE_SOFTMAX, want_raw_labels=True, impl=IMPL_STREAM)

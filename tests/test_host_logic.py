@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.View) == 32
-    assert ctypes.sizeof(_lib.FuseArgs) == 12 * 4 + 8 * 8
+    assert ctypes.sizeof(_lib.FuseArgs) == 12 * 4 + 9 * 8
     assert ctypes.sizeof(_lib.TilePos) == 16
     assert ctypes.sizeof(_lib.MosaicQuad) == 64
     assert ctypes.sizeof(_lib.MosaicPlan) == 16 + 4 * 64
