@@ -1769,6 +1769,7 @@ static bool make_static_geom(const pisto_ctx* h, const FuseParams& p, int nbuf, 
   g->aux = low ? kSAux : 0;
   g->cwarps = (kST / (2 * np) * kSS + 31) / 32;
   g->threads = g->cwarps * 32 + 32 * g->aux + 32 + ((PISTO_STATIC_DEFER && np == 2) ? 32 : 0);  // + producer warp (+ fixer warp)
+  if (np == 2 && g->threads > 512) return false;   // fuse_static_kernel's launch bound
   int fl = 0;
   for (int v = 0; v < V; v++) {
     g->view_off[v] = fl;
