@@ -33,7 +33,8 @@ __device__ __forceinline__ int identity_decide_fast(const float (&a)[C], const D
   return ok ? bi : -1;
 }
 
-template <int C>
+// RAW2: also write label_raw_out (a template parameter: the common kernel must not carry the second decision's registers)
+template <int C, bool RAW2 = false>
 __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_constant__ FuseParams p) {
   constexpr int BINS = C * C;
   __shared__ unsigned int hist[BINS];
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         for (int c = 0; c < C; c++) gr.v[c] = __ldcs(reinterpret_cast<const float4*>(base + c * hw));
       }
       if (do_conf) gr.g4 = __ldcs(reinterpret_cast<const unsigned int*>(p.gt + pix));
-      if ((p.label_out || p.label_raw_out) && p.bg) gr.bg4 = __ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix));
+      if ((p.label_out || RAW2) && p.bg) gr.bg4 = __ldcs(reinterpret_cast<const unsigned int*>(p.bg + pix));
     }
     return gr;
   };
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
     int lab[4], labr[4];
     if (!gr.scores) {
       lab[0] = lab[1] = lab[2] = lab[3] = tp.single;
-      labr[0] = labr[1] = labr[2] = labr[3] = tp.single;
+      if (RAW2) labr[0] = labr[1] = labr[2] = labr[3] = tp.single;
     } else {
       float a[4][C];
 #pragma unroll
@@ -112,8 +113,10 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         all_ok = (lab[0] | lab[1] | lab[2] | lab[3]) >= 0;
       }
       // second output (PISTO_DECIDE_RAW): where the cheap decision held, the leader's margin makes argmax(softmax) == argmax(logits)
+      if (RAW2) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) labr[j] = lab[j];
+        for (int j = 0; j < 4; j++) labr[j] = lab[j];
+      }
       if (!all_ok) {
         DecideCfg raw = p.dec;
         raw.decide_mode = PISTO_DECIDE_RAW;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
         for (int j = 0; j < 4; j++)
           if (!unmasked || lab[j] < 0) {
             lab[j] = pisto_decide<C>(a[j], tp.bits, p.dec, false, nullptr);
-            if (p.label_raw_out) labr[j] = pisto_decide<C>(a[j], tp.bits, raw, false, nullptr);
+            if (RAW2) labr[j] = pisto_decide<C>(a[j], tp.bits, raw, false, nullptr);
           }
       }
     }
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) fuse_identity_kernel(const __grid_co
       }
       *reinterpret_cast<unsigned int*>(p.label_out + pix) = o;
     }
-    if (p.label_raw_out) {
+    if (RAW2) {
       unsigned int o = (unsigned)labr[0] | ((unsigned)labr[1] << 8) | ((unsigned)labr[2] << 16) | ((unsigned)labr[3] << 24);
       if (p.bg) {
         const unsigned int eq = __vcmpeq4(gr.bg4, 0x01010101u * (unsigned)p.bg_match);
@@ -196,7 +199,7 @@ int pisto_launch_fuse_identity(pisto_ctx* h, const FuseParams& p, cudaStream_t s
   const long long cap = (long long)h->sm_count * 16;
   if (grid > cap) grid = cap;
   switch (p.C) {
-#define PISTO_ID_CASE(CC) case CC: fuse_identity_kernel<CC><<<(int)grid, kThreads, 0, st>>>(p); break;
+#define PISTO_ID_CASE(CC) case CC: if (p.label_raw_out) fuse_identity_kernel<CC, true><<<(int)grid, kThreads, 0, st>>>(p); else fuse_identity_kernel<CC, false><<<(int)grid, kThreads, 0, st>>>(p); break;
     PISTO_ID_CASE(1) PISTO_ID_CASE(2) PISTO_ID_CASE(3) PISTO_ID_CASE(4) PISTO_ID_CASE(5) PISTO_ID_CASE(6) PISTO_ID_CASE(7) PISTO_ID_CASE(8)
 #undef PISTO_ID_CASE
     default: return PISTO_OK;
