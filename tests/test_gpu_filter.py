@@ -270,3 +270,22 @@ def test_bit_stability_over_1000_launches(cuda):
         out = ops.fuse_argmax_confusion(views, cfg["codes"], (224, 224), **kw)
         bad += (out["labels"] != lab0).sum() + (out["lowres"].view(torch.int32) != low0.view(torch.int32)).sum()
     assert int(bad.item()) == 0
+
+
+def test_batch_sizes_around_the_sm_count(cuda):
+    """Tile hand-over of the shape-specialised kernel (producer warp, 13 compute warps, fixer warp of the deferred exact pass): batches
+    of 1, SMs - 1, SMs, SMs + 1, 2 SMs + 1 tiles -- CTAs with zero, one or two tiles, queues that are emptied after the last tile -- give
+    the generic kernel's labels, 32x32 logits and confusion matrix bit for bit (tools/stress_static.py runs the long version)."""
+    sms = torch.cuda.get_device_properties(cuda).multi_processor_count
+    for N in (1, sms - 1, sms, sms + 1, 2 * sms + 1):
+        for cfg, kw in ((synthetic.cfg2(N=N), dict(mask_mode=MASK_FILL, decide=DECIDE_SOFTMAX, bg_match=1, bg_label=3, lowres=(32, 32))),
+                        (synthetic.cfg3(N=N), dict(decide=DECIDE_SOFTMAX))):
+            ca = ops.new_confusion(cfg["C"], cuda) if cfg.get("gt") is not None else None
+            cb = ops.new_confusion(cfg["C"], cuda) if cfg.get("gt") is not None else None
+            a = run(cfg, cuda, 0, conf=ca, **kw)
+            b = run(cfg, cuda, IMPL_GENERIC, conf=cb, **kw)
+            assert torch.equal(a["labels"], b["labels"]), N
+            if "lowres" in b:
+                assert torch.equal(a["lowres"], b["lowres"]), N
+            if ca is not None:
+                assert torch.equal(ca, cb) and int(ca.sum()) == int((cfg["gt"] < cfg["C"]).sum()), N
